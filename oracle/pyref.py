@@ -225,6 +225,11 @@ class Port(_Engine):
 
     def __init__(self):
         super().__init__(self.PATH, "caaa_oracle_")
+        self.lib.caaa_oracle_stuck.restype = C.c_int
+
+    def stuck(self):
+        """True if the last call hit the sea-battle round guard (the reference would never return)."""
+        return bool(self.lib.caaa_oracle_stuck())
 
 
 def have_ref():
