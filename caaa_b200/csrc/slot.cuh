@@ -1,0 +1,139 @@
+// slot.cuh -- per-game working set ("slot") and the read-only tables, as they live in shared
+// memory while a CTA steps its games.
+//
+// One slot = the reference's 670-byte GameState (verbatim layout, include/caaa_types.h, reference
+// include/game_state.h:20-68) followed by the derived caches that the reference keeps in
+// file-scope globals (reference src/engine.cpp:120-159) and the per-game stream state.
+// The slot stride is an odd number of 32-bit words, so when the 32 lanes of a warp touch the
+// same field of 32 different games the accesses fall into 32 different banks.
+#pragma once
+#include <stdint.h>
+#include "../../include/caaa_types.h"
+
+#if defined(__CUDACC__)
+#define CAAA_HD __host__ __device__ __forceinline__
+#define CAAA_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define CAAA_HD inline
+#define CAAA_HD_NOINLINE
+#endif
+
+namespace caaa {
+
+constexpr int NL = CAAA_LANDS, NS = CAAA_SEAS, NA = CAAA_AIRS, NP = CAAA_PLAYERS;
+constexpr int NLT = CAAA_LAND_UNIT_TYPES, NST = CAAA_SEA_UNIT_TYPES;
+
+// unit type ids, reference include/units/units.h:19-44
+enum : int { FIGHTERS = 0, BOMBERS_LAND_AIR = 1, INFANTRY = 2, ARTILLERY = 3, TANKS = 4, AA_GUNS = 5 };
+enum : int { TRANS_EMPTY = 1, TRANS_1I, TRANS_1A, TRANS_1T, TRANS_2I, TRANS_1I_1A, TRANS_1I_1T, SUBMARINES,
+             DESTROYERS, CARRIERS, CRUISERS, BATTLESHIPS, BS_DAMAGED, BOMBERS_SEA };
+
+// Small per-unit-type tables (reference src/units.cpp) packed one byte per entry into 64-bit
+// immediates: a lookup is a shift and a mask, costs no memory access, and constant-folds when
+// the unit type is known at compile time.
+CAAA_HD constexpr uint32_t pk8(int i, uint64_t lo, uint64_t hi = 0) {
+  return (uint32_t)(((i < 8 ? lo : hi) >> (8 * (i & 7))) & 0xffu);
+}
+#define CAAA_PK(a, b, c, d, e, f, g, h)                                                                \
+  ((uint64_t)(a) | ((uint64_t)(b) << 8) | ((uint64_t)(c) << 16) | ((uint64_t)(d) << 24) |              \
+   ((uint64_t)(e) << 32) | ((uint64_t)(f) << 40) | ((uint64_t)(g) << 48) | ((uint64_t)(h) << 56))
+
+CAAA_HD constexpr uint32_t off_land(int t) { return pk8(t, CAAA_PK(4, 9, 16, 18, 20, 23, 0, 0)); }
+CAAA_HD constexpr uint32_t states_land(int t) { return pk8(t, CAAA_PK(5, 7, 2, 2, 3, 2, 0, 0)); }
+CAAA_HD constexpr uint32_t cost_land(int t) { return pk8(t, CAAA_PK(10, 14, 3, 4, 5, 5, 0, 0)); }
+CAAA_HD constexpr uint32_t weight_land(int t) { return pk8(t, CAAA_PK(255, 255, 2, 3, 3, 6, 0, 0)); }
+CAAA_HD constexpr uint32_t max_move_land(int t) { return pk8(t, CAAA_PK(4, 6, 1, 1, 2, 1, 0, 0)); }
+CAAA_HD constexpr uint32_t off_sea(int t) {
+  return pk8(t, CAAA_PK(0, 5, 9, 14, 19, 24, 28, 32), CAAA_PK(36, 39, 41, 43, 46, 49, 52, 0));
+}
+CAAA_HD constexpr uint32_t states_sea(int t) {
+  return pk8(t, CAAA_PK(5, 4, 5, 5, 5, 4, 4, 4), CAAA_PK(3, 2, 2, 3, 3, 3, 5, 0));
+}
+CAAA_HD constexpr uint32_t cost_sea(int t) {
+  return pk8(t, CAAA_PK(10, 8, 11, 12, 13, 14, 15, 16), CAAA_PK(8, 8, 14, 10, 22, 22, 14, 0));
+}
+CAAA_HD constexpr uint32_t attack_sea(int t) {
+  return pk8(t, CAAA_PK(3, 0, 0, 0, 0, 0, 0, 0), CAAA_PK(2, 2, 1, 3, 4, 4, 4, 0));
+}
+CAAA_HD constexpr uint32_t defense_sea(int t) {
+  return pk8(t, CAAA_PK(4, 0, 0, 0, 0, 0, 0, 0), CAAA_PK(1, 2, 2, 3, 4, 4, 1, 0));
+}
+CAAA_HD constexpr uint32_t staging_sea(int t) { return pk8(t, CAAA_PK(0, 1, 1, 1, 1, 0, 0, 0), 0); }
+CAAA_HD constexpr uint32_t unloading_sea(int t) { return pk8(t, CAAA_PK(0, 0, 1, 1, 1, 1, 1, 1), 0); }
+CAAA_HD constexpr uint32_t unmoved_sea(int t) {
+  return pk8(t, CAAA_PK(4, 1, 1, 1, 1, 1, 1, 1), CAAA_PK(2, 1, 1, 2, 2, 2, 255, 0));
+}
+CAAA_HD constexpr uint32_t done_moving_sea(int t) {
+  return pk8(t, CAAA_PK(0, 0, 0, 0, 0, 0, 0, 0), CAAA_PK(0, 0, 0, 1, 1, 1, 0, 0));
+}
+CAAA_HD constexpr uint32_t unload_cargo1(int t) {
+  return pk8(t, CAAA_PK(255, 255, INFANTRY, ARTILLERY, TANKS, INFANTRY, ARTILLERY, TANKS), ~0ull);
+}
+// LOAD_UNIT_TYPE rows for infantry / artillery / tanks (reference src/units.cpp:99-117), indices 0..4
+CAAA_HD constexpr uint32_t load_result(int land_type, int trans_type) {
+  return land_type == INFANTRY ? pk8(trans_type, CAAA_PK(255, TRANS_1I, TRANS_2I, TRANS_1I_1A, TRANS_1I_1T, 255, 255, 255))
+         : land_type == ARTILLERY ? pk8(trans_type, CAAA_PK(255, TRANS_1A, TRANS_1I_1A, 255, 255, 255, 255, 255))
+                                  : pk8(trans_type, CAAA_PK(255, TRANS_1T, TRANS_1I_1T, 255, 255, 255, 255, 255));
+}
+// casualty orders, reference src/engine.cpp:81-97
+CAAA_HD constexpr uint32_t order_land_def(int k) { return pk8(k, CAAA_PK(AA_GUNS, BOMBERS_LAND_AIR, INFANTRY, ARTILLERY, TANKS, FIGHTERS, 0, 0)); }
+CAAA_HD constexpr uint32_t order_sea_def(int k) {
+  return pk8(k, CAAA_PK(SUBMARINES, DESTROYERS, CARRIERS, CRUISERS, FIGHTERS, BS_DAMAGED, TRANS_EMPTY, TRANS_1I),
+             CAAA_PK(TRANS_1A, TRANS_1T, TRANS_2I, TRANS_1I_1A, TRANS_1I_1T, 0, 0, 0));
+}
+CAAA_HD constexpr uint32_t order_sea_att3(int k) {
+  return pk8(k, CAAA_PK(BS_DAMAGED, TRANS_EMPTY, TRANS_1I, TRANS_1A, TRANS_1T, TRANS_2I, TRANS_1I_1A, TRANS_1I_1T));
+}
+CAAA_HD constexpr uint32_t buy_sea(int k) { return pk8(k, CAAA_PK(FIGHTERS, TRANS_EMPTY, SUBMARINES, DESTROYERS, CARRIERS, CRUISERS, BATTLESHIPS, 0)); }
+
+// Read-only tables staged once per CTA in shared memory: the reference's topology tables plus
+// per-player-to-move team lists (refresh_allies, reference src/engine.cpp:716-725, depends only
+// on player_index, so it is tabulated instead of cached per game).
+struct DevTables {
+  CaaaTables t;
+  uint8_t allied_mask[NP];    // bit p set <=> relative player p is allied with the player to move
+  uint8_t n_enemies[NP];
+  uint8_t enemies[NP][4];     // relative indices of the enemies, ascending (casualty order depends on it)
+  uint8_t pad_[2];
+};
+
+// status bits reported per game (0 = clean)
+enum : uint32_t {
+  CAAA_ERR_SEA_ROUND_CAP = 1u,   // a sea battle exceeded SEA_ROUND_CAP rounds (the reference would never return)
+  CAAA_ERR_LOAD_FAILED = 2u,     // load_transport found no transport (the reference prints and loops)
+};
+constexpr int SEA_ROUND_CAP = 10000;
+
+struct GameSlot {
+  CaaaGameState st;   // 0..669: verbatim reference layout
+  uint8_t nvm;        // valid_moves_count
+  uint8_t canal_state;
+  // 672
+  int32_t tot_land[6][NL];  // total_player_land_units (row 5 = rotate_turns scratch)
+  int32_t tot_sea[6][NS];   // total_player_sea_units
+  int32_t enemy_count[NA];  // enemy_units_count
+  int32_t income[6];        // income_per_turn
+  int32_t large_cargo[NS];  // transports_with_large_cargo_space
+  int32_t small_cargo[NS];
+  int32_t carriers[NS];     // allied_carriers
+  int32_t answers_remaining;
+  uint32_t draws;           // random bytes consumed so far (= Philox draw index)
+  uint32_t rng[4];          // current 16-byte Philox block
+  uint32_t game_lo, game_hi;
+  int32_t turns;
+  uint32_t status;
+  int8_t nfact[6];          // total_factory_count
+  uint8_t factloc[6][NL];   // factory_locations
+  uint8_t cur_land[NL][NLT];  // current_player_land_unit_types
+  uint8_t cur_sea[NS][NST];   // current_player_sea_unit_types
+  uint8_t blockade[NS], edestroyers[NS];
+  uint8_t land_blocked[25], sea_blocked[9], sub_blocked[9];
+  uint8_t vm[CAAA_ACTIONS];   // valid_moves (persists across phases, turns: reference engine.cpp:158)
+  uint8_t use_selected, selected_action, unlucky;  // expansion mode (reference engine.cpp:156,160,163)
+  uint8_t pad_[1];
+};
+static_assert(sizeof(CaaaGameState) == 670, "GameState layout");
+static_assert(sizeof(GameSlot) % 4 == 0, "slot must be a whole number of words");
+static_assert((sizeof(GameSlot) / 4) % 2 == 1, "slot stride must be an odd number of words (bank-conflict-free)");
+
+}  // namespace caaa

@@ -232,6 +232,18 @@ class Port(_Engine):
         return bool(self.lib.caaa_oracle_stuck())
 
 
+class HostSim(_Engine):
+    """The product's device engine compiled for the host (tests/hostsim) -- CPU test tier only."""
+    PATH = os.path.join(os.path.dirname(HERE), "tests", "hostsim", "libcaaa_hostsim.so")
+
+    def __init__(self):
+        super().__init__(self.PATH, "caaa_hostsim_")
+        self.lib.caaa_hostsim_stuck.restype = C.c_int
+
+    def stuck(self):
+        return bool(self.lib.caaa_hostsim_stuck())
+
+
 def have_ref():
     return os.path.exists(Ref.PATH)
 

@@ -29,3 +29,12 @@ def port():
         import subprocess
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libcaaa_oracle.so"])
     return pyref.Port()
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    """The product's device engine compiled for the host (CPU test tier only; see tests/hostsim)."""
+    import subprocess
+    from oracle import pyref
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "hostsim")])
+    return pyref.HostSim()
