@@ -1,0 +1,135 @@
+"""ctypes binding of libcaaa_gpu.so (include/caaa_gpu.h).  No game logic lives here."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .layout import CACHE_DTYPE, STATE_BYTES, STATS_DTYPE, SUMMARY_DTYPE, TABLES_DTYPE
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcaaa_gpu.so")
+
+# every symbol include/caaa_gpu.h declares
+SYMBOLS = ["caaa_gpu_init", "caaa_gpu_shutdown", "caaa_gpu_last_error", "caaa_gpu_get_tables",
+           "caaa_gpu_device_info", "caaa_gpu_rollout_batch", "caaa_gpu_rollout_batch_device",
+           "caaa_gpu_set_stream", "caaa_gpu_random_play_until_terminal", "caaa_gpu_advance",
+           "caaa_gpu_resolve_battles", "caaa_gpu_expand", "caaa_gpu_evaluate"]
+
+
+class CaaaGpuError(RuntimeError):
+    pass
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise CaaaGpuError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    lib.caaa_gpu_init.argtypes = [i32]
+    lib.caaa_gpu_last_error.restype = C.c_char_p
+    lib.caaa_gpu_get_tables.argtypes = [vp]
+    lib.caaa_gpu_device_info.argtypes = [vp, vp, vp]
+    lib.caaa_gpu_rollout_batch.argtypes = [vp, i32, i32, u64, u64, vp, vp, vp]
+    lib.caaa_gpu_rollout_batch_device.argtypes = [vp, i32, i32, u64, u64, vp, vp, vp, vp]
+    lib.caaa_gpu_set_stream.argtypes = [u64, u64]
+    lib.caaa_gpu_random_play_until_terminal.argtypes = [vp]
+    lib.caaa_gpu_random_play_until_terminal.restype = C.c_double
+    lib.caaa_gpu_advance.argtypes = [vp, i32, u64, u64, i32, vp, vp, vp]
+    lib.caaa_gpu_resolve_battles.argtypes = [vp, i32, u64, u64, vp, vp, vp]
+    lib.caaa_gpu_expand.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.caaa_gpu_evaluate.argtypes = [vp, i32, vp]
+    return lib
+
+
+def _states(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.shape[-1] != STATE_BYTES:
+        raise ValueError("states must be (n, 670) uint8")
+    return a
+
+
+class GpuEngine:
+    """One context per process (the library keeps one context per device)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self._check(self.lib.caaa_gpu_init(device))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CaaaGpuError(f"libcaaa_gpu error {rc}: {self.lib.caaa_gpu_last_error().decode()}")
+
+    def device_info(self):
+        sm, smem = C.c_int(0), C.c_int(0)
+        name = C.create_string_buffer(64)
+        self._check(self.lib.caaa_gpu_device_info(C.byref(sm), C.byref(smem), name))
+        return {"sm_count": sm.value, "smem_per_block": smem.value, "name": name.value.decode()}
+
+    def tables(self):
+        t = np.zeros(1, dtype=TABLES_DTYPE)
+        self._check(self.lib.caaa_gpu_get_tables(t.ctypes.data))
+        return t[0]
+
+    def rollout_batch(self, states, rollouts_per_state, seed, first_game_id=0, want_stats=False):
+        states = _states(states)
+        n = states.shape[0] * int(rollouts_per_state)
+        results = np.empty(n, dtype=np.float64)
+        stats = np.zeros(n, dtype=STATS_DTYPE) if want_stats else None
+        summary = np.zeros(1, dtype=SUMMARY_DTYPE)
+        self._check(self.lib.caaa_gpu_rollout_batch(states.ctypes.data, states.shape[0], int(rollouts_per_state),
+                                                    int(seed), int(first_game_id), results.ctypes.data,
+                                                    stats.ctypes.data if want_stats else None, summary.ctypes.data))
+        return results, stats, summary[0]
+
+    def rollout_batch_device(self, d_states_ptr, n_states, rollouts_per_state, seed, first_game_id, d_results_ptr,
+                             d_stats_ptr=None, d_summary_ptr=None, stream_ptr=None):
+        """All pointers are raw device addresses (ints), e.g. torch.Tensor.data_ptr(); asynchronous on the stream."""
+        self._check(self.lib.caaa_gpu_rollout_batch_device(d_states_ptr, int(n_states), int(rollouts_per_state),
+                                                           int(seed), int(first_game_id), d_results_ptr,
+                                                           d_stats_ptr, d_summary_ptr, stream_ptr))
+
+    def set_stream(self, seed, next_game_id=0):
+        self._check(self.lib.caaa_gpu_set_stream(int(seed), int(next_game_id)))
+
+    def random_play_until_terminal(self, state):
+        state = _states(state)
+        return float(self.lib.caaa_gpu_random_play_until_terminal(state.ctypes.data))
+
+    def advance(self, states, seed, first_game_id, n_turns):
+        states = _states(states)
+        n = states.shape[0]
+        out = np.empty_like(states)
+        caches = np.zeros(n, dtype=CACHE_DTYPE)
+        draws = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.caaa_gpu_advance(states.ctypes.data, n, int(seed), int(first_game_id), int(n_turns),
+                                              out.ctypes.data, caches.ctypes.data, draws.ctypes.data))
+        return out, caches, draws
+
+    def resolve_battles(self, states, seed, first_game_id=0):
+        states = _states(states)
+        n = states.shape[0]
+        out = np.empty_like(states)
+        draws = np.zeros(n, dtype=np.int32)
+        summary = np.zeros(1, dtype=SUMMARY_DTYPE)
+        self._check(self.lib.caaa_gpu_resolve_battles(states.ctypes.data, n, int(seed), int(first_game_id),
+                                                      out.ctypes.data, draws.ctypes.data, summary.ctypes.data))
+        return out, draws, summary[0]
+
+    def expand(self, leaves, want_children=True):
+        leaves = _states(leaves)
+        n = leaves.shape[0]
+        n_actions = np.zeros(n, dtype=np.uint8)
+        actions = np.zeros((n, 20), dtype=np.uint8)
+        children = np.zeros((n, 20, STATE_BYTES), dtype=np.uint8) if want_children else None
+        status = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.caaa_gpu_expand(leaves.ctypes.data, n, n_actions.ctypes.data, actions.ctypes.data,
+                                             children.ctypes.data if want_children else None, status.ctypes.data))
+        return n_actions, actions, children, status
+
+    def evaluate(self, states):
+        states = _states(states)
+        scores = np.zeros(states.shape[0], dtype=np.float64)
+        self._check(self.lib.caaa_gpu_evaluate(states.ctypes.data, states.shape[0], scores.ctypes.data))
+        return scores

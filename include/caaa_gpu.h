@@ -1,0 +1,101 @@
+/* caaa_gpu.h -- C-ABI of the B200 rollout library (libcaaa_gpu.so).
+ *
+ * Drop-in boundary for the reference's rollout call and its two tree-expansion calls.  The
+ * reference binds these through plain C++ externs (reference src/mcts.cpp:16-22, declared in
+ * include/engine.h:150-159); INTEGRATION.md shows the shim a maintainer adds so that mcts.cpp
+ * links unchanged.  Plain pointers and sizes only; no torch types.
+ *
+ * All functions return 0 on success and a negative code on failure; the message of the last
+ * failure is available from caaa_gpu_last_error().  One context per process/device; calls are
+ * serialised by the caller (the reference API is single-threaded as well, src/engine.cpp:102-163).
+ * Unless a function says "device pointer", buffers are caller-owned host memory.
+ *
+ * There is no CPU fallback: every entry point fails with CAAA_E_NO_DEVICE when no CUDA device can
+ * be used.
+ */
+#ifndef CAAA_GPU_H
+#define CAAA_GPU_H
+
+#include "caaa_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAAA_OK 0
+#define CAAA_E_NO_DEVICE (-1)
+#define CAAA_E_CUDA (-2)
+#define CAAA_E_ARG (-3)
+#define CAAA_E_NOT_INIT (-4)
+
+/* Whole-batch counters, accumulated on the device by the rollout kernel. */
+typedef struct CaaaBatchSummary {
+  uint64_t playouts;
+  uint64_t plies;      /* player-turns stepped */
+  uint64_t decisions;  /* move / purchase / retreat draws */
+  uint64_t draws;      /* random bytes consumed (decisions + dice) */
+  uint64_t flagged;    /* playouts whose status word is non-zero (guards tripped) */
+  double sum_result;   /* sum of results, Allies' view */
+  double kernel_ms;    /* device time of the kernel(s), CUDA events on the launch stream */
+} CaaaBatchSummary;
+
+/* replaces initialize_constants() + the engine's global set-up (reference include/engine.h:29,
+ * src/engine.cpp:165-178): builds the topology tables on the host and uploads them. */
+int caaa_gpu_init(int device);
+int caaa_gpu_shutdown(void);
+const char* caaa_gpu_last_error(void);
+int caaa_gpu_get_tables(CaaaTables* out);
+int caaa_gpu_device_info(int* sm_count, int* max_smem_per_block, char* name64);
+
+/* Batched form of `double random_play_until_terminal(GameState*)` (reference include/engine.h:158,
+ * src/engine.cpp:4184-4242, called from src/mcts.cpp:94).  Plays rollouts_per_state playouts from
+ * each of n_states states.  Playout i (0 <= i < n_states*rollouts_per_state) starts from state
+ * i / rollouts_per_state and draws the byte stream of game id first_game_id + i under `seed`.
+ * results[i] is what the reference returns; stats (optional, one per playout) carries the parity
+ * side outputs; summary (optional) the whole-batch counters.  The input states are not modified. */
+int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollouts_per_state, uint64_t seed,
+                           uint64_t first_game_id, double* results, CaaaRolloutStats* stats,
+                           CaaaBatchSummary* summary);
+
+/* Same, with every buffer already resident in device memory (device pointers; stats/summary may be
+ * NULL) and asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).  d_summary must be
+ * zeroed by the caller; kernel_ms is not filled in. */
+int caaa_gpu_rollout_batch_device(const void* d_states, int n_states, int rollouts_per_state, uint64_t seed,
+                                  uint64_t first_game_id, double* d_results, CaaaRolloutStats* d_stats,
+                                  CaaaBatchSummary* d_summary, void* cuda_stream);
+
+/* Single-state shim with the reference's signature semantics (include/engine.h:158): one playout
+ * from *state with the next game id of an internal counter (caaa_gpu_set_stream sets seed and
+ * counter).  Returns the score, or NaN on failure. */
+int caaa_gpu_set_stream(uint64_t seed, uint64_t next_game_id);
+double caaa_gpu_random_play_until_terminal(const CaaaGameState* state);
+
+/* Step n states through `n_turns` whole player-turns of random play without a terminal test (the
+ * body of the loop at reference src/engine.cpp:4204-4237) and return the states and the derived
+ * caches (either output may be NULL).  Game id of state i is first_game_id + i.  Used for parity
+ * tests of the caches and to produce randomised mid-game leaves. */
+int caaa_gpu_advance(const CaaaGameState* states, int n, uint64_t seed, uint64_t first_game_id, int n_turns,
+                     CaaaGameState* out_states, CaaaCacheDump* out_caches, int32_t* out_draws);
+
+/* Isolated combat resolution (BASELINE config 3): for each state runs refresh_full_cache,
+ * resolve_sea_battles, resolve_land_battles (reference src/engine.cpp:642, 2312, 3055) with random
+ * dice and retreat decisions, game id first_game_id + i.  out_states / out_draws may be NULL. */
+int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, uint64_t first_game_id,
+                             CaaaGameState* out_states, int32_t* out_draws, CaaaBatchSummary* summary);
+
+/* Tree expansion (reference get_possible_actions + apply_action per action, include/engine.h:153-154,
+ * src/engine.cpp:4050-4183; what expand_node does, src/mcts.cpp:110-126): for each leaf the action
+ * list (n_actions[i] <= 20, actions[i*20 ..]) and, if children != NULL, the state reached by every
+ * action (children[i*20 + k]).  status[i] (optional) is non-zero when a guard tripped: the
+ * reference would not return from that expansion ("expansion-mode hangs"). */
+int caaa_gpu_expand(const CaaaGameState* leaves, int n, uint8_t* n_actions, uint8_t* actions,
+                    CaaaGameState* children, uint32_t* status);
+
+/* is_terminal_state / evaluate_state on caller-supplied states, with the unit totals taken from
+ * the states themselves (the reference reads stale globals here, src/engine.cpp:4244-4248,4314). */
+int caaa_gpu_evaluate(const CaaaGameState* states, int n, double* scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAAA_GPU_H */

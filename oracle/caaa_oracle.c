@@ -1780,3 +1780,7 @@ int caaa_oracle_stuck(void) { /* returns and clears the sea-battle guard flag */
   G.stuck = 0;
   return s;
 }
+void caaa_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { caaa_philox4x32_10_ref(ctr, key, out); }
+uint8_t caaa_oracle_stream_byte(uint64_t seed, uint64_t game_id, uint32_t draw_index) {
+  return caaa_philox_byte_ref(seed, game_id, draw_index);
+}

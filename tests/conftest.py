@@ -24,10 +24,9 @@ def ref():
 @pytest.fixture(scope="session")
 def port():
     """The plain-C oracle port (oracle/libcaaa_oracle.so)."""
+    import subprocess
     from oracle import pyref
-    if not pyref.have_port():
-        import subprocess
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libcaaa_oracle.so"])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libcaaa_oracle.so"])
     return pyref.Port()
 
 

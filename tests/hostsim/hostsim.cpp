@@ -162,3 +162,17 @@ void caaa_hostsim_get_cache(CaaaCacheDump* d) {
 }
 void caaa_hostsim_get_tables(CaaaTables* t) { *t = g_tables.t; }
 }
+extern "C" void caaa_hostsim_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+extern "C" uint8_t caaa_hostsim_stream_byte(uint64_t seed, uint64_t game_id, uint32_t draw_index) {
+  GameSlot g;
+  std::memset(&g, 0, sizeof(g));
+  g.game_lo = (uint32_t)game_id;
+  g.game_hi = (uint32_t)(game_id >> 32);
+  RunCtx cx{&g_tables, (uint32_t)seed, (uint32_t)(seed >> 32)};
+  g.draws = draw_index & ~15u;
+  uint8_t b = 0;
+  for (uint32_t d = g.draws; d <= draw_index; d++) b = next_byte(&g, cx);
+  return b;
+}

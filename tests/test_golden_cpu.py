@@ -1,0 +1,74 @@
+"""CPU tier: the oracle port and the host build of the device engine against the golden fixtures
+generated from the patched reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from caaa_b200 import synth
+from oracle import pyref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(params=["port", "hostsim"])
+def eng(request, port, hostsim):
+    return port if request.param == "port" else hostsim
+
+
+def test_start_rollouts(eng):
+    g = np.load(os.path.join(GOLD, "start_rollouts.npz"))
+    eng.set_stream(1, int(g["seed"]))
+    s0 = pyref.start_state()
+    assert np.array_equal(eng.rollout_many(s0, 0, 1024), g["stats0"][:1024])
+    assert np.array_equal(eng.rollout_many(s0, int(g["first1"]), 256), g["stats1"])
+
+
+def test_advance_and_midgame(eng):
+    a = np.load(os.path.join(GOLD, "advance.npz"))
+    m = np.load(os.path.join(GOLD, "midgame_rollouts.npz"))
+    eng.set_stream(1, int(a["seed"]))
+    s0 = pyref.start_state()
+    per_leaf = int(m["per_leaf"])
+    for i in range(len(a["turns"])):
+        eng.load_state(s0, int(a["first"]) + i)
+        for _ in range(int(a["turns"][i])):
+            for ph in range(pyref.N_PHASES):
+                eng.run_phase(ph)
+        assert np.array_equal(eng.get_state(), a["states"][i]), i
+        assert eng.draws() == a["draws"][i]
+        c = eng.get_cache()
+        for name in ("total_player_land_units", "total_player_sea_units", "enemy_units_count", "income_per_turn",
+                     "current_player_sea_unit_types", "valid_moves", "valid_moves_count", "is_land_path_blocked"):
+            assert np.array_equal(c[name], a["caches"][i][name]), (i, name)
+        st = eng.rollout_many(a["states"][i], int(m["first"]) + i * per_leaf, per_leaf)
+        assert np.array_equal(st, m["stats"][i]), i
+
+
+def test_battles(eng):
+    g = np.load(os.path.join(GOLD, "battles.npz"))
+    n = 1024
+    bs = synth.battle_states(int(g["n"]), seed=int(g["seed"]))
+    assert np.array_equal(np.array([pyref.fnv1a64(r) for r in bs[:64]], dtype=np.uint64), g["in_hash"])
+    eng.set_stream(1, int(g["seed"]))
+    for i in range(n):
+        eng.load_state(bs[i], i)
+        eng.run_phase(9)
+        eng.run_phase(11)
+        assert pyref.fnv1a64(eng.get_state()) == g["out_hash"][i], i
+        assert eng.draws() == g["draws"][i]
+
+
+def test_expansion(eng):
+    g = np.load(os.path.join(GOLD, "expansion.npz"))
+    for i in range(len(g["leaves"])):
+        acts = eng.get_possible_actions(g["leaves"][i])
+        n = int(g["n_actions"][i])
+        assert len(acts) == n and np.array_equal(acts, g["actions"][i][:n]), i
+        for k in range(n):
+            child = eng.apply_action(g["leaves"][i], acts[k])
+            if g["stuck"][i][k]:
+                assert eng.stuck()
+            else:
+                assert not eng.stuck()
+                assert pyref.fnv1a64(child) == g["child_hash"][i][k], (i, k)

@@ -1,0 +1,176 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C-ABI (libcaaa_gpu.so), against
+
+* the golden fixtures generated from the patched reference (tests/golden),
+* the oracle port on fresh seeds (sizes the oracle finishes in seconds),
+* size-independent properties at BASELINE.json's full size (1 M playouts): determinism,
+  partition invariance, counter consistency, and the distribution test against the
+  unpatched-stream reference with a stated binomial tolerance.
+
+Everything is bit-exact (integer / byte work and an IEEE double ratio) except the distribution test.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from caaa_b200 import layout, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def fnv_rows(a):
+    h = np.full(a.shape[0], 0xcbf29ce484222325, dtype=np.uint64)
+    prime = np.uint64(0x100000001b3)
+    with np.errstate(over="ignore"):
+        for j in range(a.shape[1]):
+            h = (h ^ a[:, j].astype(np.uint64)) * prime
+    return h
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from caaa_b200 import gpu
+    return gpu.GpuEngine(0)  # raises if the library or the device is missing: no fallback
+
+
+def test_device_is_blackwell(eng):
+    info = eng.device_info()
+    assert info["smem_per_block"] >= 227 * 1024
+    assert info["sm_count"] >= 100
+
+
+def test_start_rollouts_golden(eng):
+    g = np.load(os.path.join(GOLD, "start_rollouts.npz"))
+    s0 = layout.start_state()
+    res, stats, summ = eng.rollout_batch(s0, 4096, int(g["seed"]), 0, want_stats=True)
+    assert np.array_equal(stats, g["stats0"])
+    assert np.array_equal(res, g["stats0"]["result"])
+    assert summ["playouts"] == 4096 and summ["plies"] == g["stats0"]["turns"].sum()
+    assert summ["draws"] == g["stats0"]["draws"].sum() and summ["decisions"] == g["stats0"]["decisions"].sum()
+    assert summ["flagged"] == 0
+    _, stats1, _ = eng.rollout_batch(s0, 256, int(g["seed"]), int(g["first1"]), want_stats=True)
+    assert np.array_equal(stats1, g["stats1"])
+
+
+def test_start_rollouts_vs_oracle_fresh_seed(eng, port):
+    s0 = layout.start_state()
+    for seed, first, n in ((0x5EED5EED1234, 77, 2500), (3, (1 << 62) + 1, 500)):
+        port.set_stream(1, seed)
+        want = port.rollout_many(s0, first, n)
+        _, got, _ = eng.rollout_batch(s0, n, seed, first, want_stats=True)
+        assert np.array_equal(got, want)
+
+
+def test_advance_golden(eng):
+    a = np.load(os.path.join(GOLD, "advance.npz"))
+    s0 = layout.start_state()
+    for i in range(len(a["turns"])):
+        st, caches, draws = eng.advance(s0, int(a["seed"]), int(a["first"]) + i, int(a["turns"][i]))
+        assert np.array_equal(st[0], a["states"][i]), i
+        assert draws[0] == a["draws"][i]
+        for name in layout.CACHE_DTYPE.names:
+            if name in ("enemies_0", "pad_"):
+                continue
+            assert np.array_equal(caches[0][name], a["caches"][i][name]), (i, name)
+        n_en = int(caches[0]["enemies_count_0"])
+        assert np.array_equal(caches[0]["enemies_0"][:n_en], a["caches"][i]["enemies_0"][:n_en])
+
+
+def test_leaf_parallel_midgame_golden(eng):
+    a = np.load(os.path.join(GOLD, "advance.npz"))
+    m = np.load(os.path.join(GOLD, "midgame_rollouts.npz"))
+    per_leaf = int(m["per_leaf"])
+    _, stats, summ = eng.rollout_batch(a["states"], per_leaf, int(m["seed"]), int(m["first"]), want_stats=True)
+    assert np.array_equal(stats.reshape(-1, per_leaf), m["stats"])
+    assert summ["flagged"] == 0
+
+
+def test_battles_golden(eng):
+    g = np.load(os.path.join(GOLD, "battles.npz"))
+    bs = synth.battle_states(int(g["n"]), seed=int(g["seed"]))
+    out, draws, summ = eng.resolve_battles(bs, int(g["seed"]), 0)
+    assert np.array_equal(fnv_rows(out), g["out_hash"])
+    assert np.array_equal(draws, g["draws"])
+    assert summ["draws"] == g["draws"].sum() and summ["flagged"] == 0
+
+
+def test_battles_vs_oracle_ragged(eng, port):
+    """A ragged batch (not a multiple of the block size) with a different seed and id offset."""
+    bs = synth.battle_states(1000 + 37, seed=99)
+    out, draws, _ = eng.resolve_battles(bs, 4242, 10**12)
+    port.set_stream(1, 4242)
+    for i in range(0, len(bs), 5):
+        port.load_state(bs[i], 10**12 + i)
+        port.run_phase(9)
+        port.run_phase(11)
+        assert np.array_equal(port.get_state(), out[i]), i
+        assert port.draws() == draws[i]
+
+
+def test_expansion_golden(eng):
+    g = np.load(os.path.join(GOLD, "expansion.npz"))
+    n_actions, actions, children, status = eng.expand(g["leaves"])
+    assert np.array_equal(n_actions, g["n_actions"])
+    for i in range(len(n_actions)):
+        n = int(n_actions[i])
+        assert np.array_equal(actions[i][:n], g["actions"][i][:n]), i
+        ok = g["stuck"][i][:n] == 0
+        assert np.array_equal(fnv_rows(children[i][:n])[ok], g["child_hash"][i][:n][ok]), i
+        assert (status[i] != 0) == bool(g["stuck"][i][:n].any()), i
+
+
+def test_single_playout_shim(eng):
+    g = np.load(os.path.join(GOLD, "start_rollouts.npz"))
+    eng.set_stream(int(g["seed"]), 0)
+    s0 = layout.start_state()
+    for i in range(5):
+        assert eng.random_play_until_terminal(s0) == g["stats0"]["result"][i]
+
+
+def test_evaluate_matches_first_score(eng, port):
+    a = np.load(os.path.join(GOLD, "advance.npz"))
+    sc = eng.evaluate(a["states"][:32])
+    for i in range(32):
+        port.load_state(a["states"][i], 0)
+        assert port.evaluate() == sc[i]
+
+
+def test_full_size_properties_and_distribution(eng):
+    """BASELINE config 2 at full size: 1 M seeded playouts from the start position."""
+    n = 1 << 20
+    seed = 0xCAAA2024
+    s0 = layout.start_state()
+    res, stats, summ = eng.rollout_batch(s0, n, seed, 0, want_stats=True)
+    g = np.load(os.path.join(GOLD, "start_rollouts.npz"))
+    assert np.array_equal(stats[:4096], g["stats0"])
+    # determinism and partition invariance: same (seed, game id) -> same playout, however it is batched
+    res2, _, _ = eng.rollout_batch(s0, n, seed, 0)
+    assert np.array_equal(res, res2)
+    cut = 333_333
+    ra, _, _ = eng.rollout_batch(s0, cut, seed, 0)
+    rb, _, _ = eng.rollout_batch(s0, n - cut, seed, cut)
+    assert np.array_equal(np.concatenate([ra, rb]), res)
+    # counters
+    assert summ["playouts"] == n and summ["flagged"] == 0
+    assert summ["plies"] == stats["turns"].astype(np.int64).sum()
+    assert summ["draws"] == stats["draws"].astype(np.int64).sum()
+    assert summ["decisions"] == stats["decisions"].astype(np.int64).sum()
+    assert stats["turns"].min() >= 1 and stats["turns"].max() <= 1000
+    assert (res >= 0).all() and (res <= 1).all()
+    assert (stats["draws"] >= stats["decisions"]).all()
+    # distribution vs the reference on its own glibc stream (tests/golden/make_distribution.py)
+    d = np.load(os.path.join(GOLD, "distribution.npz"))
+    n_ref = float(d["n"])
+    p_ref, p_gpu = float(d["win_rate"]), float((res > 0.5).mean())
+    p = (p_ref * n_ref + p_gpu * n) / (n_ref + n)
+    sigma = np.sqrt(p * (1 - p) * (1 / n_ref + 1 / n))
+    assert abs(p_gpu - p_ref) <= 4 * sigma, (p_gpu, p_ref, sigma)            # binomial, 4 sigma
+    sd = float(res.std())
+    assert abs(res.mean() - float(d["mean_result"])) <= 4 * sd * np.sqrt(1 / n_ref + 1 / n)
+    # chi-square homogeneity on the result deciles and the game-length histogram (p > 1e-4)
+    from scipy.stats import chi2_contingency
+    dec = np.histogram(res, bins=np.linspace(0, 1, 11))[0]
+    assert chi2_contingency(np.array([dec, d["deciles"]]))[1] > 1e-4
+    th = np.histogram(stats["turns"], bins=d["turn_edges"])[0]
+    assert chi2_contingency(np.array([th, d["turn_hist"]]))[1] > 1e-4
