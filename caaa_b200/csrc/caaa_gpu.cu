@@ -1,15 +1,18 @@
 // caaa_gpu.cu -- sm_100a kernels and the C-ABI of libcaaa_gpu.so (include/caaa_gpu.h).
 //
-// Execution model: one persistent CTA per SM, one game slot per thread, all slots and
-// the topology tables resident in the CTA's 227 KB of shared memory for the whole playout, so the
-// only HBM traffic of a playout is its 670-byte start state in and its result out.  Threads pull
-// game ids from a global ticket counter and refill their slot at a turn boundary, which keeps the
-// 32 lanes of a warp in the same phase of the turn pipeline while absorbing the long tail of game
+// Execution model: one persistent CTA per SM; 192 game slots and the topology tables stay
+// resident in the CTA's 227 KB of shared memory for the whole playout, so the only HBM traffic of a
+// playout is its 670-byte start state in and its result out.  Games are regrouped by phase inside the
+// CTA: every slot carries the id of the next pipeline phase that has work for it, and each warp
+// repeatedly claims up to 32 slots waiting for the same phase (the fullest queue first), so the 32
+// lanes of a warp run the same phase function on 32 games that all have something to do in it.
+// Finished games are replaced from a global ticket counter, which absorbs the long tail of game
 // lengths.  No tensor cores: the work is branchy uint8 arithmetic.
 #include <cuda_runtime.h>
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -154,6 +157,155 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
       atomicAdd((unsigned long long*)&a.summary->draws, n_draws);
       atomicAdd((unsigned long long*)&a.summary->flagged, n_flag);
       atomicAdd(&a.summary->sum_result, sum);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase-regrouped persistent rollout kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int Q_SLOTS = 192;      // game slots per CTA
+constexpr int Q_WARPS = 8;        // more warps than slots/32: batches overlap, queues drain faster
+constexpr int Q_THREADS = Q_WARPS * 32;
+// scheduler states of a slot: 0..14 = waiting for that pipeline phase, then:
+constexpr uint32_t ST_EOT = CAAA_PH_BUY_UNITS;  // 15: purchase + end-of-turn bookkeeping + scoring (always runs)
+constexpr uint32_t ST_START = 16;               // needs a new game from the ticket counter
+constexpr uint32_t ST_BUSY = 30;                // claimed by a lane
+constexpr uint32_t ST_FREE = 31;                // no more games
+constexpr int Q_SMEM = TABLE_BYTES + Q_SLOTS * (int)sizeof(GameSlot) + Q_SLOTS * 4 + 32 * 4;
+
+struct LaneTotals {
+  unsigned long long playouts = 0, plies = 0, decisions = 0, draws = 0, flagged = 0;
+  double sum = 0.0;
+};
+
+template <bool STATS>
+__device__ __forceinline__ void finish_playout(GameSlot* g, double score, unsigned long long gi, const RolloutArgs& a, LaneTotals& tot) {
+  const double r = (g->st.player_index % 2 == 1) ? 1.0 - score : score;  // reference src/engine.cpp:4238-4241
+  a.results[gi] = r;
+  const int decisions = 100000 - g->answers_remaining;
+  if (STATS) {
+    CaaaRolloutStats s;
+    s.result = r;
+    s.turns = g->turns;
+    s.decisions = decisions;
+    s.draws = (int32_t)g->draws;
+    s.final_player = g->st.player_index;
+    s.state_hash = hash_live_state(g);
+    a.stats[gi] = s;
+  }
+  tot.playouts++;
+  tot.plies += (unsigned long long)g->turns;
+  tot.decisions += (unsigned long long)decisions;
+  tot.draws += g->draws;
+  tot.flagged += g->status != 0;
+  tot.sum += r;
+}
+
+// Run scheduler state `p` on slot g; returns the slot's next scheduler state.
+template <bool STATS>
+__device__ __forceinline__ uint32_t run_item(GameSlot* g, const RunCtx& cx, uint32_t p, const RolloutArgs& a, LaneTotals& tot) {
+  switch (p) {
+    case ST_START: {
+      const unsigned long long gi = atomicAdd(a.ticket, 1ULL);
+      if (gi >= a.n_games) return ST_FREE;
+      load_state(g, a.states + (gi / a.rollouts_per_state) * CAAA_STATE_BYTES);
+      begin_playout(g, cx, a.first_game_id + gi);
+      const double score = evaluate_state(g, cx);
+      if (!(score > 0.01 && score < 0.99)) {  // already terminal: zero turns
+        finish_playout<STATS>(g, score, gi, a, tot);
+        return ST_START;
+      }
+      return (uint32_t)next_phase_with_work(g, 0);
+    }
+    case CAAA_PH_MOVE_FIGHTERS: move_fighter_units<false>(g, cx); break;
+    case CAAA_PH_MOVE_BOMBERS: move_bomber_units<false>(g, cx); break;
+    case CAAA_PH_STAGE_TRANSPORTS: stage_transport_units<false>(g, cx); break;
+    case CAAA_PH_MOVE_TANKS: move_land_unit_type<false>(g, cx, TANKS); break;
+    case CAAA_PH_MOVE_ARTILLERY: move_land_unit_type<false>(g, cx, ARTILLERY); break;
+    case CAAA_PH_MOVE_INFANTRY: move_land_unit_type<false>(g, cx, INFANTRY); break;
+    case CAAA_PH_MOVE_TRANSPORTS: move_transport_units<false>(g, cx); break;
+    case CAAA_PH_MOVE_SUBS: move_subs<false>(g, cx); break;
+    case CAAA_PH_MOVE_SHIPS: move_destroyers_battleships<false>(g, cx); break;
+    case CAAA_PH_SEA_BATTLES: resolve_sea_battles<false>(g, cx); break;
+    case CAAA_PH_UNLOAD_TRANSPORTS: unload_transports<false>(g, cx); break;
+    case CAAA_PH_LAND_BATTLES: resolve_land_battles<false>(g, cx); break;
+    case CAAA_PH_MOVE_AA_GUNS: move_land_unit_type<false>(g, cx, AA_GUNS); break;
+    case CAAA_PH_LAND_FIGHTERS: land_fighter_units<false>(g, cx); break;
+    case CAAA_PH_LAND_BOMBERS: land_bomber_units<false>(g, cx); break;
+    default: {  // ST_EOT: reference src/engine.cpp:4229-4236
+      buy_units<false>(g, cx);
+      crash_air_units(g, cx);
+      reset_units_fully(g);
+      collect_money(g, cx);
+      rotate_turns(g, cx);
+      g->turns++;
+      const double score = evaluate_state(g, cx);
+      if (score > 0.01 && score < 0.99 && g->turns < 1000) return (uint32_t)next_phase_with_work(g, 0);
+      const unsigned long long gi = ((unsigned long long)g->game_hi << 32 | g->game_lo) - a.first_game_id;
+      finish_playout<STATS>(g, score, gi, a, tot);
+      return ST_START;
+    }
+  }
+  return (uint32_t)next_phase_with_work(g, (int)p + 1);
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(Q_THREADS, 1) rollout_kernel_regrouped(const RolloutArgs a) {
+  const DevTables* T = stage_tables(a.tables);
+  GameSlot* slots = reinterpret_cast<GameSlot*>(smem_raw + TABLE_BYTES);
+  volatile uint32_t* sstate = reinterpret_cast<volatile uint32_t*>(smem_raw + TABLE_BYTES + Q_SLOTS * sizeof(GameSlot));
+  volatile int* cnt = reinterpret_cast<volatile int*>(sstate + Q_SLOTS);  // pending slots per scheduler state
+  for (int i = threadIdx.x; i < Q_SLOTS; i += blockDim.x) sstate[i] = ST_START;
+  if (threadIdx.x < 32) cnt[threadIdx.x] = threadIdx.x == ST_START ? Q_SLOTS : 0;
+  __syncthreads();
+  const RunCtx cx{T, (uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  LaneTotals tot;
+  for (;;) {
+    // pick the fullest queue (ties: the later state, which is closer to finishing a turn)
+    const int c = lane <= (int)ST_START ? cnt[lane] : 0;
+    const unsigned key = __reduce_max_sync(0xffffffffu, c > 0 ? ((unsigned)c << 5) | (unsigned)lane : 0u);
+    if (key == 0) {
+      if (cnt[ST_FREE] >= Q_SLOTS) break;  // every slot retired
+      __nanosleep(64);
+      continue;
+    }
+    const uint32_t p = key & 31u;
+    int my = -1;
+#pragma unroll 1
+    for (int k = 0; k < Q_SLOTS / 32; k++) {
+      const int s = ((k + warp) % (Q_SLOTS / 32)) * 32 + lane;
+      if (my < 0 && sstate[s] == p && atomicCAS(const_cast<uint32_t*>(&sstate[s]), p, ST_BUSY) == p) my = s;
+    }
+    const int n = __popc(__ballot_sync(0xffffffffu, my >= 0));
+    if (lane == 0 && n > 0) atomicSub(const_cast<int*>(&cnt[p]), n);
+    if (my >= 0) {
+      __threadfence_block();
+      const uint32_t q = run_item<STATS>(slots + my, cx, p, a, tot);
+      __threadfence_block();
+      sstate[my] = q;
+      atomicAdd(const_cast<int*>(&cnt[q]), 1);
+    }
+    __syncwarp();
+  }
+  if (a.summary != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tot.playouts += __shfl_down_sync(0xffffffffu, tot.playouts, o);
+      tot.plies += __shfl_down_sync(0xffffffffu, tot.plies, o);
+      tot.decisions += __shfl_down_sync(0xffffffffu, tot.decisions, o);
+      tot.draws += __shfl_down_sync(0xffffffffu, tot.draws, o);
+      tot.flagged += __shfl_down_sync(0xffffffffu, tot.flagged, o);
+      tot.sum += __shfl_down_sync(0xffffffffu, tot.sum, o);
+    }
+    if (lane == 0) {
+      atomicAdd((unsigned long long*)&a.summary->playouts, tot.playouts);
+      atomicAdd((unsigned long long*)&a.summary->plies, tot.plies);
+      atomicAdd((unsigned long long*)&a.summary->decisions, tot.decisions);
+      atomicAdd((unsigned long long*)&a.summary->draws, tot.draws);
+      atomicAdd((unsigned long long*)&a.summary->flagged, tot.flagged);
+      atomicAdd(&a.summary->sum_result, tot.sum);
     }
   }
 }
@@ -349,6 +501,7 @@ struct Context {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long seed = 0, next_game_id = 0;
+  bool lockstep = false;
 };
 static Context g_ctx;
 static std::string g_err;
@@ -395,12 +548,21 @@ static int launch_rollout(const void* d_states, unsigned long long n_games, unsi
   a.stats = d_stats;
   a.summary = d_summary;
   a.ticket = c.d_ticket;
-  const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
-  const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
-  if (d_stats)
-    rollout_kernel<true><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
-  else
-    rollout_kernel<false><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
+  if (c.lockstep) {  // first-generation kernel, kept for A/B measurements (CAAA_ROLLOUT_KERNEL=lockstep)
+    const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
+    if (d_stats)
+      rollout_kernel<true><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
+    else
+      rollout_kernel<false><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
+  } else {
+    const unsigned long long want = (n_games + Q_SLOTS - 1) / Q_SLOTS;
+    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
+    if (d_stats)
+      rollout_kernel_regrouped<true><<<grid, Q_THREADS, Q_SMEM, stream>>>(a);
+    else
+      rollout_kernel_regrouped<false><<<grid, Q_THREADS, Q_SMEM, stream>>>(a);
+  }
   CUDA_TRY(cudaGetLastError());
   return CAAA_OK;
 }
@@ -437,6 +599,12 @@ int caaa_gpu_init(int device) {
   CUDA_TRY(cudaEventCreate(&c.ev1));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_regrouped<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_regrouped<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
+  {
+    const char* k = std::getenv("CAAA_ROLLOUT_KERNEL");
+    c.lockstep = k != nullptr && std::strcmp(k, "lockstep") == 0;
+  }
   CUDA_TRY(cudaFuncSetAttribute(advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(actions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));

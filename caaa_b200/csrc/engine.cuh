@@ -49,7 +49,7 @@ CAAA_HD void clear_move_history(GameSlot* g) {  // engine.cpp:1330
   for (int i = 0; i < 32; i++) p[i] = 0;
 }
 
-CAAA_HD uint8_t next_byte(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE uint8_t next_byte(GameSlot* g, const RunCtx& cx) {
   const uint32_t d = g->draws++;
   const uint32_t k = d & 15u;
   if (k == 0) philox4x32_10(d >> 4, g->game_lo, g->game_hi, 0u, cx.seed_lo, cx.seed_hi, g->rng);
@@ -112,12 +112,12 @@ CAAA_HD void refresh_paths_blocked(GameSlot* g, const RunCtx& cx) {  // 785-814
       g->sub_blocked[s * NS + d] = g->edestroyers[n1] > 0 && g->edestroyers[n2] > 0;
     }
 }
-CAAA_HD void refresh_eot_cache(GameSlot* g, const RunCtx& cx) {  // 653-660 (refresh_allies is tabulated)
+CAAA_HD_NOINLINE void refresh_eot_cache(GameSlot* g, const RunCtx& cx) {  // 653-660 (refresh_allies is tabulated)
   refresh_canals(g, cx);
   refresh_enemy_armies_and_fleets(g, cx);
   refresh_paths_blocked(g, cx);
 }
-CAAA_HD void refresh_full_cache(GameSlot* g, const RunCtx& cx) {  // 642-652, 661-715
+CAAA_HD_NOINLINE void refresh_full_cache(GameSlot* g, const RunCtx& cx) {  // 642-652, 661-715
   for (int p = 0; p < NP; p++) {
     g->income[p] = 0;
     g->nfact[p] = 0;
@@ -177,7 +177,7 @@ CAAA_HD uint8_t defender_hits(GameSlot* g, const RunCtx& cx, int dmg) {  // 2567
   return (uint8_t)(dmg / 6 + ((int)(next_byte(g, cx) % 6) < dmg % 6 ? 1 : 0));
 }
 
-CAAA_HD void update_move_history_4air(GameSlot* g, uint8_t src, uint8_t dst) {  // 1300-1328: starts one past the list
+CAAA_HD_NOINLINE void update_move_history_4air(GameSlot* g, uint8_t src, uint8_t dst) {  // 1300-1328: starts one past the list
   for (;;) {
     const uint8_t va = g->nvm < CAAA_ACTIONS ? g->vm[g->nvm] : (uint8_t)0;
     if (va == dst) break;
@@ -188,7 +188,7 @@ CAAA_HD void update_move_history_4air(GameSlot* g, uint8_t src, uint8_t dst) {  
   }
 }
 
-CAAA_HD bool load_transport(GameSlot* g, int ut, int src_land, int dst_sea, int land_state) {  // 1397-1443
+CAAA_HD_NOINLINE bool load_transport(GameSlot* g, int ut, int src_land, int dst_sea, int land_state) {  // 1397-1443
   for (int tt = weight_land(ut) > 2 ? TRANS_1I : TRANS_1T; tt >= TRANS_EMPTY; tt--) {
     uint8_t* arr = sea_ptr(g, dst_sea, tt);
     const int unl = unloading_sea(tt);
@@ -212,7 +212,7 @@ CAAA_HD bool load_transport(GameSlot* g, int ut, int src_land, int dst_sea, int 
   return false;
 }
 
-CAAA_HD void add_valid_land_moves(GameSlot* g, const RunCtx& cx, int src, int moves, int ut) {  // 1445-1516
+CAAA_HD_NOINLINE void add_valid_land_moves(GameSlot* g, const RunCtx& cx, int src, int moves, int ut) {  // 1445-1516
   const CaaaTables& t = cx.T->t;
   uint32_t n = g->nvm;
   if (moves == 2) {
@@ -253,7 +253,7 @@ CAAA_HD void add_valid_land_moves(GameSlot* g, const RunCtx& cx, int src, int mo
   g->nvm = (uint8_t)n;
 }
 
-CAAA_HD void add_valid_sea_moves(GameSlot* g, const RunCtx& cx, int src_sea, int moves, const uint8_t* blocked) {  // 1518-1586
+CAAA_HD_NOINLINE void add_valid_sea_moves(GameSlot* g, const RunCtx& cx, int src_sea, int moves, const uint8_t* blocked) {  // 1518-1586
   const CaaaTables& t = cx.T->t;
   const int cs = g->canal_state, sa = src_sea + NL;
   uint32_t n = g->nvm;
@@ -275,7 +275,7 @@ CAAA_HD void add_valid_sea_moves(GameSlot* g, const RunCtx& cx, int src_sea, int
 }
 
 // ---- conquer_land, 1918-1984 ----
-CAAA_HD void conquer_land(GameSlot* g, const RunCtx& cx, int dst) {
+CAAA_HD_NOINLINE void conquer_land(GameSlot* g, const RunCtx& cx, int dst) {
   const CaaaTables& t = cx.T->t;
   const int pi = pidx(g);
   const int old = g->st.land_state[dst].owner_idx;
@@ -301,7 +301,7 @@ CAAA_HD void conquer_land(GameSlot* g, const RunCtx& cx, int dst) {
 
 // ---- phase 0: move_fighter_units, 1657-1803, 3385-3407 ----
 // returns bit masks (bit a = air location a): lo byte canFighterLandHere, next byte canFighterLandIn1Move
-CAAA_HD uint32_t fighter_landing_masks(GameSlot* g, const RunCtx& cx) {  // pre_move_fighter_units 1657-1714
+CAAA_HD_NOINLINE uint32_t fighter_landing_masks(GameSlot* g, const RunCtx& cx) {  // pre_move_fighter_units 1657-1714
   const CaaaTables& t = cx.T->t;
   uint32_t here = 0;
   for (int l = 0; l < NL; l++) {
@@ -330,7 +330,7 @@ CAAA_HD uint32_t fighter_landing_masks(GameSlot* g, const RunCtx& cx) {  // pre_
   return here | (in1 << 8);
 }
 template <bool EXPAND>
-CAAA_HD bool move_fighter_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_fighter_units(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   bool processed = false;
   uint32_t masks = 0;
@@ -400,7 +400,7 @@ CAAA_HD uint32_t bomber_here_mask(const GameSlot* g, const RunCtx& cx) {  // 180
   return here;
 }
 template <bool EXPAND>
-CAAA_HD bool move_bomber_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_bomber_units(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   // has-work shortcut: the landing masks are phase-local in this implementation (the reference keeps
   // them in globals, but re-derives them before every use), so nothing happens without unmoved bombers
@@ -471,7 +471,7 @@ CAAA_HD bool move_bomber_units(GameSlot* g, const RunCtx& cx) {
 
 // ---- phase 2: stage_transport_units, 1588-1655 ----
 template <bool EXPAND>
-CAAA_HD bool stage_transport_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool stage_transport_units(GameSlot* g, const RunCtx& cx) {
   bool processed = false;
   for (int ut = TRANS_EMPTY; ut <= TRANS_1T; ut++) {
     const int staging = states_sea(ut) - 1, done = staging - 1;
@@ -522,7 +522,7 @@ CAAA_HD bool stage_transport_units(GameSlot* g, const RunCtx& cx) {
 
 // ---- phases 3,4,5,12: move_land_unit_type, 1986-2060 ----
 template <bool EXPAND>
-CAAA_HD bool move_land_unit_type(GameSlot* g, const RunCtx& cx, int ut) {
+CAAA_HD_NOINLINE bool move_land_unit_type(GameSlot* g, const RunCtx& cx, int ut) {
   const CaaaTables& t = cx.T->t;
   bool processed = false;
   for (int src = 0; src < NL; src++)
@@ -579,7 +579,7 @@ CAAA_HD bool move_land_unit_type(GameSlot* g, const RunCtx& cx, int ut) {
 
 // ---- phase 6: move_transport_units, 2062-2159 ----
 template <bool EXPAND>
-CAAA_HD bool move_transport_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_transport_units(GameSlot* g, const RunCtx& cx) {
   bool processed = false;
   for (int s = 0; s < NS; s++) {  // skip_empty_transports 2062-2075
     uint8_t* e = sea_ptr(g, s, TRANS_EMPTY);
@@ -637,7 +637,7 @@ CAAA_HD bool move_transport_units(GameSlot* g, const RunCtx& cx) {
 
 // ---- phase 7: move_subs, 2160-2214 ----
 template <bool EXPAND>
-CAAA_HD bool move_subs(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_subs(GameSlot* g, const RunCtx& cx) {
   bool processed = false;
   for (int s = 0; s < NS; s++) {
     uint8_t* arr = sea_ptr(g, s, SUBMARINES);
@@ -688,7 +688,7 @@ CAAA_HD void carry_allied_fighters(GameSlot* g, const RunCtx& cx, int src, int d
   }
 }
 template <bool EXPAND>
-CAAA_HD bool move_destroyers_battleships(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_destroyers_battleships(GameSlot* g, const RunCtx& cx) {
   bool processed = false;
   for (int ut = DESTROYERS; ut <= BS_DAMAGED; ut++) {
     const int unmoved = unmoved_sea(ut), done = done_moving_sea(ut);
@@ -742,7 +742,7 @@ CAAA_HD bool take_hits(uint8_t* n, uint32_t& hits, uint32_t& taken) {
   taken = hits;
   return true;
 }
-CAAA_HD void remove_land_defenders(GameSlot* g, const RunCtx& cx, int land, uint32_t hits) {  // 2613-2641
+CAAA_HD_NOINLINE void remove_land_defenders(GameSlot* g, const RunCtx& cx, int land, uint32_t hits) {  // 2613-2641
   const int pi = pidx(g), ne = cx.T->n_enemies[pi];
   for (int k = 0; k < 6; k++) {
     const int ut = order_land_def(k);
@@ -758,7 +758,7 @@ CAAA_HD void remove_land_defenders(GameSlot* g, const RunCtx& cx, int land, uint
     }
   }
 }
-CAAA_HD void remove_land_attackers(GameSlot* g, int land, uint32_t hits) {  // 2642-2698
+CAAA_HD_NOINLINE void remove_land_attackers(GameSlot* g, int land, uint32_t hits) {  // 2642-2698
   for (int ut = INFANTRY; ut <= TANKS; ut++) {  // ORDER_OF_LAND_ATTACKERS_1, state 0 only
     uint8_t* n = &land_ptr(g, land, ut)[0];
     if (*n == 0) continue;
@@ -784,7 +784,7 @@ CAAA_HD void remove_land_attackers(GameSlot* g, int land, uint32_t hits) {  // 2
     }
   }
 }
-CAAA_HD void remove_sea_defenders(GameSlot* g, const RunCtx& cx, int sea, uint32_t hits, bool submerged) {  // 2700-2806
+CAAA_HD_NOINLINE void remove_sea_defenders(GameSlot* g, const RunCtx& cx, int sea, uint32_t hits, bool submerged) {  // 2700-2806
   const int pi = pidx(g), ne = cx.T->n_enemies[pi], air = sea + NL;
   for (int e = 0; e < ne; e++) {  // battleships absorb one hit each
     uint8_t* su = g->st.other_sea_units[cx.T->enemies[pi][e] - 1][sea];
@@ -830,7 +830,7 @@ CAAA_HD bool hit_sea_state0(GameSlot* g, int sea, int ut, uint32_t& hits) {
   }
   return done;
 }
-CAAA_HD void remove_sea_attackers(GameSlot* g, int sea, uint32_t hits) {  // 2808-2982
+CAAA_HD_NOINLINE void remove_sea_attackers(GameSlot* g, int sea, uint32_t hits) {  // 2808-2982
   uint8_t* bb = &sea_ptr(g, sea, BATTLESHIPS)[0];
   if (*bb > 0) {
     uint32_t taken;
@@ -881,7 +881,7 @@ CAAA_HD void sea_retreat(GameSlot* g, int src, int dst) {  // 2582-2603
   g->st.flagged_for_combat[src + NL] = 0;
 }
 template <bool EXPAND>
-CAAA_HD bool resolve_sea_battles(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool resolve_sea_battles(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   const int pi = pidx(g), ne = cx.T->n_enemies[pi];
   for (int s = 0; s < NS; s++) {
@@ -1000,7 +1000,7 @@ CAAA_HD bool resolve_sea_battles(GameSlot* g, const RunCtx& cx) {
 
 // ---- phase 10: unload_transports, 2984-3053, 3373-3383 ----
 template <bool EXPAND>
-CAAA_HD bool unload_transports(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool unload_transports(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   bool processed = false;
   for (int ut = TRANS_1I; ut <= TRANS_1I_1T; ut++) {
@@ -1068,7 +1068,7 @@ CAAA_HD void hit_air_states(GameSlot* g, int land, int ut, int lo, int hi, uint3
   }
 }
 template <bool EXPAND>
-CAAA_HD bool resolve_land_battles(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool resolve_land_battles(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   const int pi = pidx(g), ne = cx.T->n_enemies[pi];
   for (int l = 0; l < NL; l++) {
@@ -1191,7 +1191,7 @@ CAAA_HD uint32_t fighter_final_landing_mask(GameSlot* g, const RunCtx& cx) {  //
   return here;
 }
 template <bool EXPAND>
-CAAA_HD bool land_fighter_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool land_fighter_units(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   bool processed = false;
   uint32_t here = 0;
@@ -1243,7 +1243,7 @@ CAAA_HD bool land_fighter_units(GameSlot* g, const RunCtx& cx) {
   return false;
 }
 template <bool EXPAND>
-CAAA_HD bool land_bomber_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool land_bomber_units(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   bool processed = false;
   uint32_t here = 0;
@@ -1295,7 +1295,7 @@ CAAA_HD bool land_bomber_units(GameSlot* g, const RunCtx& cx) {
 
 // ---- phase 15: buy_units (purchase and placement), 3663-3834 ----
 template <bool EXPAND>
-CAAA_HD bool buy_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool buy_units(GameSlot* g, const RunCtx& cx) {
   const CaaaTables& t = cx.T->t;
   for (int f = 0; f < g->nfact[0] && f < 256; f++) {
     const int land = g->factloc[0][f];
@@ -1404,7 +1404,7 @@ CAAA_HD bool buy_units(GameSlot* g, const RunCtx& cx) {
 }
 
 // ---- phases 16-19: crash_air_units, reset_units_fully, collect_money, 3836-3894 ----
-CAAA_HD void crash_air_units(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE void crash_air_units(GameSlot* g, const RunCtx& cx) {
   const uint32_t here = fighter_landing_masks(g, cx);
   for (int l = 0; l < NL; l++) {
     if ((here >> l) & 1) continue;
@@ -1443,7 +1443,7 @@ CAAA_HD void collect_money(GameSlot* g, const RunCtx& cx) {
 }
 
 // ---- phase 20: rotate_turns, 3895-4029 ----
-CAAA_HD void rotate_turns(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE void rotate_turns(GameSlot* g, const RunCtx& cx) {
   CaaaGameState* st = &g->st;
   // per-player unit totals: current <- other[0] <- other[1] <- other[2] <- other[3] <- current
   for (int l = 0; l < NL; l++)
@@ -1509,7 +1509,7 @@ CAAA_HD void rotate_turns(GameSlot* g, const RunCtx& cx) {
 }
 
 // ---- scoring, 4301-4337 ----
-CAAA_HD double evaluate_state(GameSlot* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE double evaluate_state(GameSlot* g, const RunCtx& cx) {
   const uint8_t starting = g->st.player_index;
   const int pi = starting >= NP ? starting - NP : starting;
   int allied_score = 1 + g->st.money[0], enemy_score = 1;  // 4309+4311: the mover's money counts twice
@@ -1564,6 +1564,14 @@ CAAA_HD bool run_phase(GameSlot* g, const RunCtx& cx, int ph) {
 // Prepare a slot whose `st` has just been filled: what random_play_until_terminal does before its
 // loop (4185-4203, with P1 iv and the P2 stream reset).
 CAAA_HD void begin_playout(GameSlot* g, const RunCtx& cx, uint64_t game_id) {
+  // entries of the path-blocked tables that no refresh ever writes are read by the flat-index quirk
+  // (add_valid_land_moves); they are zero in the reference because its globals are zero-initialised
+  for (int i = 0; i < 25; i++) g->land_blocked[i] = 0;
+  for (int i = 0; i < 9; i++) g->sea_blocked[i] = g->sub_blocked[i] = 0;
+  for (int p = 0; p < 6; p++)
+    for (int l = 0; l < NL; l++) g->factloc[p][l] = 0;
+  g->income[5] = 0;
+  g->nfact[5] = 0;
   refresh_full_cache(g, cx);
   g->answers_remaining = 100000;
   g->use_selected = 0;
@@ -1586,6 +1594,90 @@ CAAA_HD uint64_t hash_live_state(const GameSlot* g) {  // FNV-1a-64 over the fir
     h *= CAAA_FNV_PRIME;
   }
   return h;
+}
+
+// ---- phase routing -------------------------------------------------------------------------------
+// A phase of the pipeline is a no-op on a game unless some unit is still in a state that the phase
+// moves (the reference relies on the same property for its stop-and-resume expansion mode: every
+// phase is idempotent on "done" units).  phase_has_work(p) is true exactly when
+// phase p would touch the slot; next_phase_with_work() lets the scheduler queue a game only for
+// phases that do something.  Phases >= CAAA_PH_BUY_UNITS always run (end-of-turn work item).
+CAAA_HD bool phase_has_work(const GameSlot* g, int ph) {
+  const CaaaGameState& st = g->st;
+  uint32_t any = 0;
+  switch (ph) {
+    case CAAA_PH_MOVE_FIGHTERS:
+      for (int l = 0; l < NL; l++) any |= st.land_state[l].fighters[4];
+      for (int s = 0; s < NS; s++) any |= st.units_sea[s].fighters[4];
+      break;
+    case CAAA_PH_MOVE_BOMBERS:
+      for (int l = 0; l < NL; l++) any |= st.land_state[l].bombers[6];
+      break;
+    case CAAA_PH_STAGE_TRANSPORTS:
+      for (int s = 0; s < NS; s++)
+        any |= st.units_sea[s].trans_empty[3] | st.units_sea[s].trans_1i[4] | st.units_sea[s].trans_1a[4] | st.units_sea[s].trans_1t[4];
+      break;
+    case CAAA_PH_MOVE_TANKS:
+      for (int l = 0; l < NL; l++) any |= st.land_state[l].tanks[1] | st.land_state[l].tanks[2];
+      break;
+    case CAAA_PH_MOVE_ARTILLERY:
+      for (int l = 0; l < NL; l++) any |= st.land_state[l].artillery[1];
+      break;
+    case CAAA_PH_MOVE_INFANTRY:
+      for (int l = 0; l < NL; l++) any |= st.land_state[l].infantry[1];
+      break;
+    case CAAA_PH_MOVE_TRANSPORTS:
+      for (int s = 0; s < NS; s++) {
+        const CaaaUnitsSea& u = st.units_sea[s];
+        any |= u.trans_empty[1] | u.trans_empty[2] | u.trans_empty[3];  // skip_empty_transports
+        any |= u.trans_1i[2] | u.trans_1i[3] | u.trans_1a[2] | u.trans_1a[3] | u.trans_1t[2] | u.trans_1t[3];
+        any |= u.trans_2i[2] | u.trans_2i[3] | u.trans_1i_1a[2] | u.trans_1i_1a[3] | u.trans_1i_1t[2] | u.trans_1i_1t[3];
+      }
+      break;
+    case CAAA_PH_MOVE_SUBS:
+      for (int s = 0; s < NS; s++) any |= st.units_sea[s].submarines[2];
+      break;
+    case CAAA_PH_MOVE_SHIPS:
+      for (int s = 0; s < NS; s++) {
+        const CaaaUnitsSea& u = st.units_sea[s];
+        any |= u.destroyers[1] | u.carriers[1] | u.cruisers[2] | u.battleships[2] | u.bs_damaged[2];
+      }
+      break;
+    case CAAA_PH_SEA_BATTLES:
+      for (int s = 0; s < NS; s++) any |= (st.flagged_for_combat[NL + s] != 0 && g->tot_sea[0][s] != 0);
+      break;
+    case CAAA_PH_UNLOAD_TRANSPORTS:
+      for (int s = 0; s < NS; s++) {
+        const CaaaUnitsSea& u = st.units_sea[s];
+        any |= u.trans_1i[1] | u.trans_1a[1] | u.trans_1t[1] | u.trans_2i[1] | u.trans_1i_1a[1] | u.trans_1i_1t[1];
+      }
+      break;
+    case CAAA_PH_LAND_BATTLES:
+      for (int l = 0; l < NL; l++) any |= (st.flagged_for_combat[l] != 0 && g->tot_land[0][l] != 0);
+      break;
+    case CAAA_PH_MOVE_AA_GUNS:
+      for (int l = 0; l < NL; l++) any |= st.land_state[l].aa_guns[1];
+      break;
+    case CAAA_PH_LAND_FIGHTERS:
+      for (int l = 0; l < NL; l++) any |= st.land_state[l].fighters[1] | st.land_state[l].fighters[2] | st.land_state[l].fighters[3];
+      for (int s = 0; s < NS; s++) any |= st.units_sea[s].fighters[1] | st.units_sea[s].fighters[2] | st.units_sea[s].fighters[3];
+      break;
+    case CAAA_PH_LAND_BOMBERS:
+      for (int l = 0; l < NL; l++)
+        for (int k = 1; k <= 5; k++) any |= st.land_state[l].bombers[k];
+      for (int s = 0; s < NS; s++)
+        for (int k = 0; k <= 4; k++) any |= st.units_sea[s].bombers[k];
+      break;
+    default:
+      return true;
+  }
+  return any != 0;
+}
+// first phase >= from that has work; CAAA_PH_BUY_UNITS (the end-of-turn item) if none
+CAAA_HD int next_phase_with_work(const GameSlot* g, int from) {
+  for (int ph = from; ph < CAAA_PH_BUY_UNITS; ph++)
+    if (phase_has_work(g, ph)) return ph;
+  return CAAA_PH_BUY_UNITS;
 }
 
 }  // namespace caaa

@@ -176,3 +176,29 @@ extern "C" uint8_t caaa_hostsim_stream_byte(uint64_t seed, uint64_t game_id, uin
   for (uint32_t d = g.draws; d <= draw_index; d++) b = next_byte(&g, cx);
   return b;
 }
+// playout driven the way the queue scheduler drives it: only phases with work are executed
+extern "C" void caaa_hostsim_rollout_many_routed(const void* s, int64_t first, int n, CaaaRolloutStats* st) {
+  for (int i = 0; i < n; i++) {
+    GameSlot* g = &g_slot;
+    std::memcpy(&g->st, s, CAAA_STATE_BYTES);
+    begin_playout(g, g_cx, (uint64_t)first + (uint64_t)i);
+    double score = evaluate_state(g, g_cx);
+    while (score > 0.01 && score < 0.99 && g->turns < 1000) {
+      int ph = next_phase_with_work(g, 0);
+      while (ph < CAAA_PH_BUY_UNITS) {
+        run_phase<false>(g, g_cx, ph);
+        ph = next_phase_with_work(g, ph + 1);
+      }
+      for (ph = CAAA_PH_BUY_UNITS; ph < CAAA_PH_COUNT; ph++) run_phase<false>(g, g_cx, ph);
+      g->turns++;
+      score = evaluate_state(g, g_cx);
+    }
+    if (g->st.player_index % 2 == 1) score = 1 - score;
+    st[i].result = score;
+    st[i].turns = g->turns;
+    st[i].decisions = 100000 - g->answers_remaining;
+    st[i].draws = (int32_t)g->draws;
+    st[i].final_player = g->st.player_index;
+    st[i].state_hash = hash_live_state(g);
+  }
+}
