@@ -202,6 +202,90 @@ __device__ __forceinline__ void finish_playout(GameSlot* g, double score, unsign
   tot.sum += r;
 }
 
+// Block-synchronous variant of the lockstep kernel: a barrier after every phase keeps all warps of the
+// CTA inside the same phase function at the same time, so they share its instructions in the SM's
+// instruction caches (the whole pipeline is ~240 KB of SASS; one phase is 5-30 KB).
+#define CAAA_SYNC_PHASE(call) \
+  do {                        \
+    if (run) { call; }        \
+    __syncthreads();          \
+  } while (0)
+template <bool STATS, int LANES, int SLOTS = ROLLOUT_THREADS>
+__global__ void __launch_bounds__(SLOTS / LANES * 32, ROLLOUT_THREADS / SLOTS) rollout_kernel_sync(const RolloutArgs a) {
+  // Only the first LANES lanes of every warp own a game slot.  The kernel is bound by per-warp
+  // latency and by the serialised union of divergent control flow, not by issue slots, so fewer
+  // games per warp (a shorter union) and more warps per SM (more latency hiding) is the better trade.
+  const DevTables* T = stage_tables(a.tables);
+  const int lane = threadIdx.x & 31;
+  const bool owner = lane < LANES;
+  GameSlot* g = reinterpret_cast<GameSlot*>(smem_raw + TABLE_BYTES) + ((threadIdx.x >> 5) * LANES + (owner ? lane : 0));
+  const RunCtx cx{T, (uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+  bool live = false, exhausted = !owner;
+  unsigned long long gi = 0;
+  double score = 0.0;
+  LaneTotals tot;
+  for (;;) {
+    if (!live && !exhausted) {
+      gi = atomicAdd(a.ticket, 1ULL);
+      if (gi < a.n_games) {
+        load_state(g, a.states + (gi / a.rollouts_per_state) * CAAA_STATE_BYTES);
+        begin_playout(g, cx, a.first_game_id + gi);
+        score = evaluate_state(g, cx);
+        live = true;
+      } else {
+        exhausted = true;
+      }
+    }
+    if (!__syncthreads_or(live)) break;
+    const bool run = live && score > 0.01 && score < 0.99 && g->turns < 1000;
+    if (live && !run) {
+      finish_playout<STATS>(g, score, gi, a, tot);
+      live = false;
+    }
+    CAAA_SYNC_PHASE(move_fighter_units<false>(g, cx));
+    CAAA_SYNC_PHASE(move_bomber_units<false>(g, cx));
+    CAAA_SYNC_PHASE(stage_transport_units<false>(g, cx));
+    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, TANKS));
+    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, ARTILLERY));
+    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, INFANTRY));
+    CAAA_SYNC_PHASE(move_transport_units<false>(g, cx));
+    CAAA_SYNC_PHASE(move_subs<false>(g, cx));
+    CAAA_SYNC_PHASE(move_destroyers_battleships<false>(g, cx));
+    CAAA_SYNC_PHASE(resolve_sea_battles<false>(g, cx));
+    CAAA_SYNC_PHASE(unload_transports<false>(g, cx));
+    CAAA_SYNC_PHASE(resolve_land_battles<false>(g, cx));
+    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, AA_GUNS));
+    CAAA_SYNC_PHASE(land_fighter_units<false>(g, cx));
+    CAAA_SYNC_PHASE(land_bomber_units<false>(g, cx));
+    CAAA_SYNC_PHASE(buy_units<false>(g, cx));
+    CAAA_SYNC_PHASE(crash_air_units(g, cx); reset_units_fully(g); collect_money(g, cx));
+    CAAA_SYNC_PHASE(rotate_turns(g, cx));
+    if (run) {
+      g->turns++;
+      score = evaluate_state(g, cx);
+    }
+  }
+  if (a.summary != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tot.playouts += __shfl_down_sync(0xffffffffu, tot.playouts, o);
+      tot.plies += __shfl_down_sync(0xffffffffu, tot.plies, o);
+      tot.decisions += __shfl_down_sync(0xffffffffu, tot.decisions, o);
+      tot.draws += __shfl_down_sync(0xffffffffu, tot.draws, o);
+      tot.flagged += __shfl_down_sync(0xffffffffu, tot.flagged, o);
+      tot.sum += __shfl_down_sync(0xffffffffu, tot.sum, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd((unsigned long long*)&a.summary->playouts, tot.playouts);
+      atomicAdd((unsigned long long*)&a.summary->plies, tot.plies);
+      atomicAdd((unsigned long long*)&a.summary->decisions, tot.decisions);
+      atomicAdd((unsigned long long*)&a.summary->draws, tot.draws);
+      atomicAdd((unsigned long long*)&a.summary->flagged, tot.flagged);
+      atomicAdd(&a.summary->sum_result, tot.sum);
+    }
+  }
+}
+
 // Run scheduler state `p` on slot g; returns the slot's next scheduler state.
 template <bool STATS>
 __device__ __forceinline__ uint32_t run_item(GameSlot* g, const RunCtx& cx, uint32_t p, const RolloutArgs& a, LaneTotals& tot) {
@@ -501,7 +585,8 @@ struct Context {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long seed = 0, next_game_id = 0;
-  bool lockstep = false;
+  bool lockstep = false, sync = true, regrouped = false;
+  int lanes = 8, ctas_per_sm = 1;
 };
 static Context g_ctx;
 static std::string g_err;
@@ -548,7 +633,34 @@ static int launch_rollout(const void* d_states, unsigned long long n_games, unsi
   a.stats = d_stats;
   a.summary = d_summary;
   a.ticket = c.d_ticket;
-  if (c.lockstep) {  // first-generation kernel, kept for A/B measurements (CAAA_ROLLOUT_KERNEL=lockstep)
+  if (c.sync) {
+    const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
+#define CAAA_LAUNCH_SYNC(L)                                                                             \
+  do {                                                                                                 \
+    if (d_stats)                                                                                       \
+      rollout_kernel_sync<true, L><<<grid, ROLLOUT_THREADS / L * 32, rollout_smem(), stream>>>(a);     \
+    else                                                                                               \
+      rollout_kernel_sync<false, L><<<grid, ROLLOUT_THREADS / L * 32, rollout_smem(), stream>>>(a);    \
+  } while (0)
+    if (c.ctas_per_sm > 1) {  // several smaller CTAs per SM: one CTA's barrier waits overlap another's work
+      const int slots = c.ctas_per_sm == 2 ? 96 : 64;
+      const unsigned long long want2 = (n_games + slots - 1) / slots;
+      const unsigned long long cap = (unsigned long long)c.sm_count * c.ctas_per_sm;
+      const int grid2 = (int)(want2 < cap ? want2 : cap);
+      const int smem2 = TABLE_BYTES + slots * (int)sizeof(GameSlot);
+      if (c.ctas_per_sm == 2) {
+        if (d_stats) rollout_kernel_sync<true, 8, 96><<<grid2, 96 / 8 * 32, smem2, stream>>>(a);
+        else rollout_kernel_sync<false, 8, 96><<<grid2, 96 / 8 * 32, smem2, stream>>>(a);
+      } else {
+        if (d_stats) rollout_kernel_sync<true, 8, 64><<<grid2, 64 / 8 * 32, smem2, stream>>>(a);
+        else rollout_kernel_sync<false, 8, 64><<<grid2, 64 / 8 * 32, smem2, stream>>>(a);
+      }
+    } else if (c.lanes == 32) CAAA_LAUNCH_SYNC(32);
+    else if (c.lanes == 16) CAAA_LAUNCH_SYNC(16);
+    else if (c.lanes == 6) CAAA_LAUNCH_SYNC(6);
+    else CAAA_LAUNCH_SYNC(8);
+  } else if (c.lockstep) {  // first-generation kernel, kept for A/B measurements (CAAA_ROLLOUT_KERNEL=lockstep)
     const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
     const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
     if (d_stats)
@@ -604,6 +716,24 @@ int caaa_gpu_init(int device) {
   {
     const char* k = std::getenv("CAAA_ROLLOUT_KERNEL");
     c.lockstep = k != nullptr && std::strcmp(k, "lockstep") == 0;
+    c.regrouped = k != nullptr && std::strcmp(k, "regrouped") == 0;
+    c.sync = !c.lockstep && !c.regrouped;  // default: block-synchronous phases
+    const char* l = std::getenv("CAAA_LANES");
+    c.lanes = l ? std::atoi(l) : 8;
+    const char* cp = std::getenv("CAAA_CTAS_PER_SM");
+    c.ctas_per_sm = cp ? std::atoi(cp) : 1;
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 8, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 96 * (int)sizeof(GameSlot)));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 8, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 96 * (int)sizeof(GameSlot)));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 64 * (int)sizeof(GameSlot)));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 64 * (int)sizeof(GameSlot)));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   }
   CUDA_TRY(cudaFuncSetAttribute(advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
