@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) actions_kernel(const DevTables*
   const int k = g->nvm < CAAA_ACTIONS ? g->nvm : CAAA_ACTIONS;
   n_actions[i] = (uint8_t)k;
   for (int j = 0; j < CAAA_ACTIONS; j++) actions[(size_t)i * CAAA_ACTIONS + j] = j < k ? g->vm[j] : 0;
-  if (status) status[i] = g->status;
+  if (status) status[i] = g->status ? 0x80000000u : 0u;  // bit 31: the action list itself tripped a guard
 }
 __global__ void __launch_bounds__(SMALL_THREADS) apply_kernel(const DevTables* tables, const uint8_t* leaves, int n,
                                                               const uint8_t* n_actions, const uint8_t* actions,
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) apply_kernel(const DevTables* t
   begin_expansion(g, cx, 1, 1, actions[(size_t)i * CAAA_ACTIONS + k]);
   run_until_decision(g, cx);
   store_state(g, children + (size_t)idx * CAAA_STATE_BYTES);
-  if (status && g->status) atomicOr(&status[i], g->status);
+  if (status && g->status) atomicOr(&status[i], 1u << k);  // bit k: child k tripped a guard
 }
 __global__ void __launch_bounds__(SMALL_THREADS) evaluate_kernel(const DevTables* tables, const uint8_t* states, int n, double* scores) {
   const DevTables* T = stage_tables(tables);

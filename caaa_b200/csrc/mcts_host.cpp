@@ -1,0 +1,164 @@
+// mcts_host.cpp -- host-side UCT search that drives the GPU engine (product code, plain C++).
+//
+// Mirrors the reference's search loop (reference src/mcts.cpp:29-126,247-258): UCT with
+// EXPLORATION_CONSTANT 1.414 and +1 smoothing (mcts.cpp:24,47-63), expansion of every visited
+// leaf (mcts.cpp:84-87,110-126), a uniformly random child, rollout, and back-propagation in which a
+// node accumulates `result` when its parent's player_index is even and `1 - result` otherwise
+// (mcts.cpp:96-105).  What changes is where the work runs: expansion (get_possible_actions +
+// apply_action per action) and rollouts are batched device calls, `rollouts_per_leaf` playouts are
+// played per visited leaf (BASELINE config 4: 4096) and `leaves_per_batch` leaves are selected per
+// launch with virtual visits so one host thread keeps the GPU busy.  With both set to 1 the loop is
+// the reference's, except that is_terminal_state is evaluated on the node's own unit totals (the
+// reference reads stale globals there) and the random stream is Philox.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <random>
+#include <vector>
+
+#include "../../include/caaa_gpu.h"
+#include "../../include/caaa_host.h"
+
+namespace {
+
+constexpr double kExploration = 1.414;  // reference src/mcts.cpp:24
+
+struct Node {
+  CaaaGameState state;
+  uint8_t action = 0;
+  Node* parent = nullptr;
+  std::vector<Node*> children;
+  int64_t visits = 0;
+  int64_t pending = 0;  // virtual visits of leaves selected in the current batch
+  double value = 0.0;
+  bool in_batch = false;
+};
+
+struct Tree {
+  std::deque<Node> pool;  // stable addresses
+  Node* make(const CaaaGameState& s, uint8_t action, Node* parent) {
+    pool.emplace_back();
+    Node* n = &pool.back();
+    n->state = s;
+    n->action = action;
+    n->parent = parent;
+    return n;
+  }
+};
+
+Node* select_best_leaf(Node* node) {  // reference src/mcts.cpp:47-63, with virtual visits
+  while (!node->children.empty()) {
+    double best = -INFINITY;
+    Node* best_child = nullptr;
+    const double n_parent = (double)(node->visits + node->pending);
+    for (Node* c : node->children) {
+      const double n = (double)(c->visits + c->pending);
+      const double uct = c->value / (n + 1) + kExploration * std::sqrt(std::log(n_parent + 1) / (n + 1));
+      if (uct > best) {
+        best = uct;
+        best_child = c;
+      }
+    }
+    node = best_child;
+  }
+  return node;
+}
+
+void backpropagate(Node* node, double sum_result, int64_t n) {  // reference src/mcts.cpp:96-105
+  while (node != nullptr) {
+    node->visits += n;
+    if (node->parent != nullptr && node->parent->state.player_index % 2 == 0) node->value += sum_result;
+    else node->value += (double)n - sum_result;
+    node = node->parent;
+  }
+}
+
+}  // namespace
+
+extern "C" int caaa_mcts_search(const CaaaGameState* root_state, int64_t iterations, int rollouts_per_leaf,
+                                int leaves_per_batch, uint64_t seed, CaaaRootStats* out, uint8_t* best_action) {
+  if (!root_state || !out || iterations < 0 || rollouts_per_leaf <= 0 || leaves_per_batch <= 0) return CAAA_E_ARG;
+  Tree tree;
+  Node* root = tree.make(*root_state, 0, nullptr);
+  std::mt19937_64 rng(seed ^ 0x9E3779B97F4A7C15ull);
+  uint64_t next_game_id = 0;
+  int64_t done = 0, playouts = 0;
+  std::vector<Node*> leaves, targets;
+  std::vector<CaaaGameState> states, children;
+  std::vector<double> scores, results;
+  std::vector<uint8_t> n_actions, actions;
+  std::vector<uint32_t> status;
+  while (done < iterations) {
+    // 1. select up to leaves_per_batch distinct leaves, marking virtual visits along their paths
+    leaves.clear();
+    const int64_t want = std::min<int64_t>(leaves_per_batch, iterations - done);
+    for (int64_t b = 0; b < want; b++) {
+      Node* leaf = select_best_leaf(root);
+      if (leaf->in_batch) break;  // the tree offers no further distinct leaf right now
+      leaf->in_batch = true;
+      for (Node* n = leaf; n != nullptr; n = n->parent) n->pending++;
+      leaves.push_back(leaf);
+    }
+    const int nl = (int)leaves.size();
+    // 2. terminal test and expansion of all selected leaves in one device call each
+    states.resize(nl);
+    for (int i = 0; i < nl; i++) states[i] = leaves[i]->state;
+    scores.resize(nl);
+    int rc = caaa_gpu_evaluate(states.data(), nl, scores.data());
+    if (rc != CAAA_OK) return rc;
+    n_actions.assign(nl, 0);
+    actions.assign((size_t)nl * CAAA_ACTIONS, 0);
+    children.resize((size_t)nl * CAAA_ACTIONS);
+    status.assign(nl, 0);
+    rc = caaa_gpu_expand(states.data(), nl, n_actions.data(), actions.data(), children.data(), status.data());
+    if (rc != CAAA_OK) return rc;
+    targets.assign(nl, nullptr);
+    for (int i = 0; i < nl; i++) {
+      Node* leaf = leaves[i];
+      const bool terminal = scores[i] > 0.99 || scores[i] < 0.01;  // reference src/engine.cpp:4244-4248
+      if (!terminal && !(status[i] & 0x80000000u)) {
+        for (int k = 0; k < n_actions[i]; k++) {
+          if (status[i] & (1u << k)) continue;  // the reference would never return from this apply_action
+          leaf->children.push_back(tree.make(children[(size_t)i * CAAA_ACTIONS + k], actions[(size_t)i * CAAA_ACTIONS + k], leaf));
+        }
+      }
+      targets[i] = leaf->children.empty() ? leaf : leaf->children[rng() % leaf->children.size()];
+      states[i] = targets[i]->state;
+    }
+    // 3. rollouts_per_leaf playouts from every target in one launch
+    results.resize((size_t)nl * rollouts_per_leaf);
+    rc = caaa_gpu_rollout_batch(states.data(), nl, rollouts_per_leaf, seed, next_game_id, results.data(), nullptr, nullptr);
+    if (rc != CAAA_OK) return rc;
+    next_game_id += (uint64_t)nl * (uint64_t)rollouts_per_leaf;
+    // 4. clear the virtual visits and back-propagate
+    for (int i = 0; i < nl; i++) {
+      for (Node* n = leaves[i]; n != nullptr; n = n->parent) n->pending--;
+      leaves[i]->in_batch = false;
+      double sum = 0.0;
+      for (int r = 0; r < rollouts_per_leaf; r++) sum += results[(size_t)i * rollouts_per_leaf + r];
+      backpropagate(targets[i], sum, rollouts_per_leaf);
+    }
+    done += nl;
+    playouts += (int64_t)nl * rollouts_per_leaf;
+  }
+  std::memset(out, 0, sizeof(*out));
+  out->n_children = (int32_t)std::min<size_t>(root->children.size(), CAAA_ACTIONS);
+  double best = -INFINITY;
+  uint8_t best_a = 255;
+  for (int i = 0; i < out->n_children; i++) {
+    const Node* c = root->children[i];
+    out->actions[i] = c->action;
+    out->visits[i] = c->visits;
+    out->values[i] = c->value;
+    if (c->value > best) {  // select_best_action, reference src/mcts.cpp:247-258
+      best = c->value;
+      best_a = c->action;
+    }
+  }
+  out->iterations = done;
+  out->playouts = playouts;
+  out->nodes = (int64_t)tree.pool.size();
+  if (best_action) *best_action = best_a;
+  return CAAA_OK;
+}

@@ -86,8 +86,9 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
 /* Tree expansion (reference get_possible_actions + apply_action per action, include/engine.h:153-154,
  * src/engine.cpp:4050-4183; what expand_node does, src/mcts.cpp:110-126): for each leaf the action
  * list (n_actions[i] <= 20, actions[i*20 ..]) and, if children != NULL, the state reached by every
- * action (children[i*20 + k]).  status[i] (optional) is non-zero when a guard tripped: the
- * reference would not return from that expansion ("expansion-mode hangs"). */
+ * action (children[i*20 + k]).  status[i] (optional) is non-zero when a guard tripped, i.e. the
+ * reference would not return from that call ("expansion-mode hangs"): bit k = applying
+ * action k, bit 31 = computing the action list itself. */
 int caaa_gpu_expand(const CaaaGameState* leaves, int n, uint8_t* n_actions, uint8_t* actions,
                     CaaaGameState* children, uint32_t* status);
 

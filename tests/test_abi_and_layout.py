@@ -25,10 +25,21 @@ def test_header_symbols_exported():
         import __graft_entry__
         __graft_entry__.build()
     lib = gpu.load_library()
+    from caaa_b200 import host
     header = open(os.path.join(ROOT, "include", "caaa_gpu.h")).read()
     declared = sorted(set(re.findall(r"\b(caaa_gpu_\w+)\s*\(", header)))
     assert declared == sorted(gpu.SYMBOLS)
-    for name in declared:
+    header2 = open(os.path.join(ROOT, "include", "caaa_host.h")).read()
+    declared2 = sorted(set(re.findall(r"\b(caaa_(?:state|mcts)_\w+)\s*\(", header2)))
+    assert declared2 == sorted(host.SYMBOLS)
+    for name in declared + declared2:
+        assert hasattr(lib, name), name
+    # the reference-named C++ entry points of caaa_engine_compat.h (Itanium-mangled)
+    for name in ("_Z20initialize_constantsv", "_Z14load_game_dataPKc", "_Z19get_game_state_copyv",
+                 "_Z11clone_stateP13CaaaGameState", "_Z10free_stateP13CaaaGameState",
+                 "_Z20get_possible_actionsP13CaaaGameStatePhPA20_h", "_Z12apply_actionP13CaaaGameStateh",
+                 "_Z17is_terminal_stateP13CaaaGameState", "_Z14evaluate_stateP13CaaaGameState",
+                 "_Z26random_play_until_terminalP13CaaaGameState"):
         assert hasattr(lib, name), name
 
 

@@ -170,3 +170,41 @@ def test_full_size_properties_and_distribution(eng):
     assert chi2_contingency(np.array([dec, d["deciles"]]))[1] > 1e-4
     th = np.histogram(stats["turns"], bins=d["turn_edges"])[0]
     assert chi2_contingency(np.array([th, d["turn_hist"]]))[1] > 1e-4
+
+
+def test_reference_named_api_drop_in(eng, tmp_path):
+    """The reference's API names (caaa_engine_compat.h) against SURVEY.md Appendix E's root expansion and
+    the golden rollouts: what mcts.cpp / main.cpp would see after switching libraries."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "compat_driver")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "compat_driver.cpp"), "-o", exe,
+                           "-L" + os.path.join(root, "caaa_b200"), "-lcaaa_gpu", "-Wl,-rpath," + os.path.join(root, "caaa_b200")])
+    out = subprocess.check_output([exe, os.path.join(GOLD, "start_position.json")], text=True).splitlines()
+    assert out[0] == "actions 6 5 4 3 2 0"
+    assert out[1:7] == ["child 6 player 1 money0 20 terminal 0", "child 5 player 0 money0 5 terminal 0",
+                        "child 4 player 0 money0 5 terminal 0", "child 3 player 0 money0 6 terminal 0",
+                        "child 2 player 0 money0 7 terminal 0", "child 0 player 1 money0 20 terminal 0"]
+    g = np.load(os.path.join(GOLD, "start_rollouts.npz"))
+    got = [float(l.split()[1]) for l in out[7:11]]
+    assert got == g["stats0"]["result"][:4].tolist()
+
+
+def test_mcts_search_on_gpu(eng):
+    from caaa_b200 import host
+    s0 = layout.start_state()
+    # reference-shaped loop: one leaf, one rollout per iteration
+    a, v, x, best, info = host.mcts_search(eng, s0, 3000, rollouts_per_leaf=1, leaves_per_batch=1, seed=11)
+    assert a.tolist() == [6, 5, 4, 3, 2, 0]            # root expansion, SURVEY.md Appendix E
+    assert v.sum() == 3000 and info["playouts"] == 3000
+    assert (x >= 0).all() and (x <= v).all()
+    # same seed -> same tree
+    a2, v2, x2, best2, _ = host.mcts_search(eng, s0, 3000, 1, 1, seed=11)
+    assert np.array_equal(v, v2) and np.array_equal(x, x2) and best == best2
+    # leaf-parallel + batched leaves (BASELINE config 4 shape)
+    a3, v3, x3, best3, info3 = host.mcts_search(eng, s0, 512, rollouts_per_leaf=256, leaves_per_batch=16, seed=5)
+    assert v3.sum() == 512 * 256 and info3["playouts"] == 512 * 256
+    assert best3 in a3.tolist()
+    # pure purchases of the first mover cannot change the material ratio much: all children's means are close
+    means = x3 / np.maximum(v3, 1)
+    assert means.max() - means.min() < 0.2

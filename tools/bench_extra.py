@@ -1,0 +1,115 @@
+#!/usr/bin/env python3
+"""Secondary measurements (BASELINE.json configs 3, 4, 5); bench.py is the headline (config 2).
+
+    python tools/bench_extra.py battles [--n 10485760]
+    python tools/bench_extra.py leaf    [--leaves 1024 --rollouts 4096]
+    [torchrun --nproc-per-node N] python tools/bench_extra.py mcts [--iterations 2048 --rollouts 4096 --leaves-per-batch 64]
+
+Each prints one JSON line.  Timing: CUDA events inside the library (kernel_ms) and wall clock around
+the C-ABI call (host buffers, copies included).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from caaa_b200 import gpu, host, layout, synth  # noqa: E402
+
+
+def battles(args):
+    eng = gpu.GpuEngine(0)
+    chunk = min(args.n, 1 << 20)
+    states = synth.battle_states(chunk, seed=0xBA77)  # the sweep reuses one generated chunk with fresh game ids
+    eng.resolve_battles(states[:4096], 0xBA77, 0)
+    done, k_ms, draws = 0, 0.0, 0
+    t0 = time.perf_counter()
+    while done < args.n:
+        n = min(chunk, args.n - done)
+        _, d, summ = eng.resolve_battles(states[:n], 0xBA77, done)
+        k_ms += float(summ["kernel_ms"])
+        draws += int(summ["draws"])
+        done += n
+    wall = time.perf_counter() - t0
+    print(json.dumps({"workload": "config 3: isolated battle resolution sweep", "battles": done,
+                      "battles_per_sec_kernel": done / (k_ms * 1e-3), "battles_per_sec_e2e": done / wall,
+                      "hbm_gbs_kernel": done * 1340 / (k_ms * 1e-3) / 1e9, "mean_draws": draws / done}))
+
+
+def leaf(args):
+    eng = gpu.GpuEngine(0)
+    s0 = layout.start_state()
+    # randomised mid-game leaves made on the device: game g advanced 1 + (g * 7) % 60 turns of random play
+    leaves = np.zeros((args.leaves, layout.STATE_BYTES), dtype=np.uint8)
+    for t in range(60):
+        idx = np.nonzero((1 + (np.arange(args.leaves) * 7) % 60) == t + 1)[0]
+        for i in idx:
+            leaves[i] = eng.advance(s0, 0x1EAF, int(i), t + 1)[0][0]
+    eng.rollout_batch(leaves[:64], 64, 0x1EAF, 0)
+    t0 = time.perf_counter()
+    res, _, summ = eng.rollout_batch(leaves, args.rollouts, 0x1EAF, 0)
+    wall = time.perf_counter() - t0
+    n = args.leaves * args.rollouts
+    print(json.dumps({"workload": "config 4: leaf-parallel rollouts from randomised mid-game states", "leaves": args.leaves,
+                      "rollouts_per_leaf": args.rollouts, "playouts_per_sec_kernel": n / (float(summ["kernel_ms"]) * 1e-3),
+                      "playouts_per_sec_e2e": n / wall, "plies_per_playout": float(summ["plies"]) / n,
+                      "flagged": int(summ["flagged"]), "mean_result": float(res.mean())}))
+
+
+def mcts(args):
+    import torch
+    import torch.distributed as dist
+    from caaa_b200 import root_parallel
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = gpu.GpuEngine(local)
+    s0 = layout.start_state()
+
+    def search(state, iterations, seed):
+        a, v, x, _, info = host.mcts_search(eng, state, iterations, args.rollouts, args.leaves_per_batch, seed)
+        search.info = info
+        return a, v, x
+
+    search(s0, args.leaves_per_batch, 1)  # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a, v, x, best = root_parallel.root_parallel_search(search, s0, args.iterations, 0xCAAA, device=torch.device("cuda", local))
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=torch.device("cuda", local))
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        total = int(v.sum())
+        print(json.dumps({"workload": "config 5: root-parallel MCTS from the start position, root statistics all-reduced",
+                          "n_gpus": world, "iterations_per_gpu": args.iterations, "rollouts_per_leaf": args.rollouts,
+                          "leaves_per_batch": args.leaves_per_batch, "playouts": total, "seconds": float(dt.item()),
+                          "playouts_per_sec": total / float(dt.item()), "root_actions": a.tolist(), "root_visits": v.tolist(),
+                          "root_mean_value": (x / np.maximum(v, 1)).round(4).tolist(), "best_action": best}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["battles", "leaf", "mcts"])
+    ap.add_argument("--n", type=int, default=10 * (1 << 20))
+    ap.add_argument("--leaves", type=int, default=1024)
+    ap.add_argument("--rollouts", type=int, default=4096)
+    ap.add_argument("--iterations", type=int, default=1024)
+    ap.add_argument("--leaves-per-batch", type=int, default=64)
+    args = ap.parse_args()
+    {"battles": battles, "leaf": leaf, "mcts": mcts}[args.what](args)
+
+
+if __name__ == "__main__":
+    main()
