@@ -86,6 +86,7 @@ struct RolloutArgs {
   CaaaRolloutStats* stats;  // optional
   CaaaBatchSummary* summary;  // optional
   unsigned long long* ticket;
+  int debug;
 };
 
 template <bool STATS>
@@ -394,6 +395,10 @@ __global__ void __launch_bounds__(Q_THREADS, 1) rollout_kernel_regrouped(const R
   }
 }
 
+}  // namespace caaa
+#include "stream_kernel.cuh"
+namespace caaa {
+
 // ---- cache dump shared by the advance kernel ----
 __device__ void dump_cache(const GameSlot* g, const DevTables* T, CaaaCacheDump* d) {
   const int pi = pidx(g);
@@ -585,8 +590,14 @@ struct Context {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long seed = 0, next_game_id = 0;
-  bool lockstep = false, sync = true, regrouped = false;
+  bool lockstep = false, sync = true, regrouped = false, streaming = false;
   int lanes = 8, ctas_per_sm = 1;
+  // device-wide phase queues + game pool of the streaming kernel (allocated on first use)
+  PhaseQueues* d_queues = nullptr;
+  unsigned long long* d_cells = nullptr;
+  PoolSlot* d_pool = nullptr;
+  unsigned pool_size = 0;
+  int pool_mult = 2;
 };
 static Context g_ctx;
 static std::string g_err;
@@ -633,7 +644,43 @@ static int launch_rollout(const void* d_states, unsigned long long n_games, unsi
   a.stats = d_stats;
   a.summary = d_summary;
   a.ticket = c.d_ticket;
-  if (c.sync) {
+  a.debug = std::getenv("CAAA_DEBUG") != nullptr;
+  if (c.streaming) {
+    const unsigned long long want = (n_games + STREAM_SLOTS - 1) / STREAM_SLOTS;
+    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
+    const unsigned need = (unsigned)c.sm_count * STREAM_SLOTS * (unsigned)c.pool_mult;
+    if (c.d_pool == nullptr || c.pool_size < need) {
+      if (c.d_pool) { cudaFree(c.d_pool); cudaFree(c.d_cells); cudaFree(c.d_queues); c.d_pool = nullptr; }
+      unsigned cap = 1;
+      while (cap < need) cap <<= 1;
+      CUDA_TRY(cudaMalloc(&c.d_pool, (size_t)need * sizeof(PoolSlot)));
+      CUDA_TRY(cudaMalloc(&c.d_cells, (size_t)NQ * cap * sizeof(unsigned long long)));
+      CUDA_TRY(cudaMalloc(&c.d_queues, sizeof(PhaseQueues)));
+      CUDA_TRY(cudaMemset(c.d_cells, 0, (size_t)NQ * cap * sizeof(unsigned long long)));
+      PhaseQueues h;
+      std::memset(&h, 0, sizeof(h));
+      h.capacity = cap;
+      h.pool_size = need;
+      h.cells = c.d_cells;
+      h.pool = c.d_pool;
+      CUDA_TRY(cudaMemcpy(c.d_queues, &h, sizeof(h), cudaMemcpyHostToDevice));
+      c.pool_size = need;
+    }
+    // queue positions keep counting across launches (cells are tagged with them); only the per-launch counters reset
+    queues_reset_kernel<<<1, 32, 0, stream>>>(c.d_queues);
+    // a launch with fewer CTAs than the pool was sized for simply uses fewer pool entries
+    if (d_stats)
+      rollout_kernel_stream<true><<<grid, STREAM_THREADS + 32, rollout_smem(), stream>>>(a, c.d_queues);
+    else
+      rollout_kernel_stream<false><<<grid, STREAM_THREADS + 32, rollout_smem(), stream>>>(a, c.d_queues);
+    if (a.debug) {
+      PhaseQueues h;
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(&h, c.d_queues, sizeof(h), cudaMemcpyDeviceToHost);
+      std::fprintf(stderr, "stream dbg: items %llu empty_polls %llu ticket_wait_polls %llu switches %llu busy_frac %.3f aborted %d\n",
+                   h.dbg[0], h.dbg[1], h.dbg[2], h.dbg[3], h.dbg[5] ? (double)h.dbg[4] / (double)h.dbg[5] : 0.0, h.aborted);
+    }
+  } else if (c.sync) {
     const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
     const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
 #define CAAA_LAUNCH_SYNC(L)                                                                             \
@@ -717,7 +764,12 @@ int caaa_gpu_init(int device) {
     const char* k = std::getenv("CAAA_ROLLOUT_KERNEL");
     c.lockstep = k != nullptr && std::strcmp(k, "lockstep") == 0;
     c.regrouped = k != nullptr && std::strcmp(k, "regrouped") == 0;
-    c.sync = !c.lockstep && !c.regrouped;  // default: block-synchronous phases
+    c.streaming = k != nullptr && std::strcmp(k, "stream") == 0;
+    c.sync = !c.lockstep && !c.regrouped && !c.streaming;  // default: block-synchronous phases
+    const char* pm = std::getenv("CAAA_POOL_MULT");
+    c.pool_mult = pm ? std::atoi(pm) : 2;
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
     const char* l = std::getenv("CAAA_LANES");
     c.lanes = l ? std::atoi(l) : 8;
     const char* cp = std::getenv("CAAA_CTAS_PER_SM");
