@@ -87,6 +87,7 @@ struct RolloutArgs {
   CaaaBatchSummary* summary;  // optional
   unsigned long long* ticket;
   int debug;
+  int groups;  // barrier sub-groups per CTA (block-synchronous kernel)
 };
 
 template <bool STATS>
@@ -206,13 +207,29 @@ __device__ __forceinline__ void finish_playout(GameSlot* g, double score, unsign
 // Block-synchronous variant of the lockstep kernel: a barrier after every phase keeps all warps of the
 // CTA inside the same phase function at the same time, so they share its instructions in the SM's
 // instruction caches (the whole pipeline is ~240 KB of SASS; one phase is 5-30 KB).
-#define CAAA_SYNC_PHASE(call) \
-  do {                        \
-    if (run) { call; }        \
-    __syncthreads();          \
+// CTA sub-group barriers (hardware named barriers 1..GROUPS): the warps of one group stay in the same
+// phase function; different groups may drift apart by whole phases, which shortens every barrier wait
+// (max over fewer games) at the price of a few more phases live in the instruction cache.
+__device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ bool group_or(int id, int count, bool pred) {
+  int out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(out)
+      : "r"((int)pred), "r"(id), "r"(count)
+      : "memory");
+  return out != 0;
+}
+#define CAAA_SYNC_PHASE(call)    \
+  do {                           \
+    if (run) { call; }           \
+    group_sync(bar_id, bar_cnt); \
   } while (0)
 template <bool STATS, int LANES, int SLOTS = ROLLOUT_THREADS>
 __global__ void __launch_bounds__(SLOTS / LANES * 32, ROLLOUT_THREADS / SLOTS) rollout_kernel_sync(const RolloutArgs a) {
+  const int n_groups = a.groups;
+  const int warps_per_group = (SLOTS / LANES) / n_groups;
+  const int bar_id = 1 + (int)(threadIdx.x >> 5) / warps_per_group, bar_cnt = warps_per_group * 32;
   // Only the first LANES lanes of every warp own a game slot.  The kernel is bound by per-warp
   // latency and by the serialised union of divergent control flow, not by issue slots, so fewer
   // games per warp (a shorter union) and more warps per SM (more latency hiding) is the better trade.
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(SLOTS / LANES * 32, ROLLOUT_THREADS / SLOTS) r
         exhausted = true;
       }
     }
-    if (!__syncthreads_or(live)) break;
+    if (!group_or(bar_id, bar_cnt, live)) break;
     const bool run = live && score > 0.01 && score < 0.99 && g->turns < 1000;
     if (live && !run) {
       finish_playout<STATS>(g, score, gi, a, tot);
@@ -591,7 +608,7 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long seed = 0, next_game_id = 0;
   bool lockstep = false, sync = true, regrouped = false, streaming = false;
-  int lanes = 8, ctas_per_sm = 1;
+  int lanes = 8, ctas_per_sm = 1, groups = 1;
   // device-wide phase queues + game pool of the streaming kernel (allocated on first use)
   PhaseQueues* d_queues = nullptr;
   unsigned long long* d_cells = nullptr;
@@ -645,6 +662,7 @@ static int launch_rollout(const void* d_states, unsigned long long n_games, unsi
   a.summary = d_summary;
   a.ticket = c.d_ticket;
   a.debug = std::getenv("CAAA_DEBUG") != nullptr;
+  a.groups = c.groups;
   if (c.streaming) {
     const unsigned long long want = (n_games + STREAM_SLOTS - 1) / STREAM_SLOTS;
     const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
@@ -772,6 +790,8 @@ int caaa_gpu_init(int device) {
     CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
     const char* l = std::getenv("CAAA_LANES");
     c.lanes = l ? std::atoi(l) : 8;
+    const char* gp = std::getenv("CAAA_GROUPS");
+    c.groups = gp ? std::atoi(gp) : 1;
     const char* cp = std::getenv("CAAA_CTAS_PER_SM");
     c.ctas_per_sm = cp ? std::atoi(cp) : 1;
     CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 8, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 96 * (int)sizeof(GameSlot)));
