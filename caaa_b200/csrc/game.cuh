@@ -1,0 +1,239 @@
+// game.cuh -- per-game working set ("Game") of the rollout engine, import/export to the reference layout.
+//
+// The reference keeps a 670-byte GameState in which every per-player array is *rotated* by one
+// player each turn (reference src/engine.cpp:3895-4029) plus ~600 bytes of derived caches in
+// file-scope globals (src/engine.cpp:120-159).  On the GPU the rotation is pure data movement that
+// every lane would repeat every ply, so a Game stores per-player data in ABSOLUTE player order and
+// never rotates; "relative player p" of the reference is absolute player (cur + p) % 5.  The
+// reference layout only exists at the ABI: import_state() / export_state() convert.
+//
+// Layout rules: 924 bytes = 231 words (odd, so the 32 lanes of a warp touching the same field of 32
+// games hit 32 different banks); every array that is scanned word-wise starts on a word boundary;
+// per-player unit totals are one 72-byte vector per player (30 land + 42 sea counts) so that scoring
+// is 18 dp4a per player against a constant cost vector.
+#pragma once
+#include <cstddef>
+#include "philox.cuh"
+#include "slot.cuh"
+
+namespace caaa {
+namespace e2 {
+
+constexpr int UT_BYTES = NL * NLT + NS * (NST - 1);  // 72: [land][6 types] then [sea][14 types]
+constexpr int LU_ROW = 21, SU_ROW = 57;              // per-location bytes of the mover's per-state counts
+
+struct Game {
+  uint32_t rng[4];            // current 16-byte Philox block
+  uint32_t draws;             // random bytes consumed so far (= Philox draw index)
+  uint32_t game_lo, game_hi;
+  int32_t answers_remaining;
+  uint32_t work;              // bit ph set => pipeline phase ph (0..14) may have something to do
+  uint32_t land_blocked;      // is_land_path_blocked, bit src*5+dst (flat, 25 bits)
+  uint32_t seasub_blocked;    // bits 0..8 is_sea_path_blocked[src*3+dst], bits 16..24 is_sub_path_blocked
+  uint32_t skipped[2];        // skipped_moves as 64 one-bit flags, flat index a*8+b
+  uint16_t turns, status;
+  int16_t tot_land[NP][NL];   // total_player_land_units, absolute player
+  int16_t tot_sea[NP][NS];    // total_player_sea_units
+  int16_t enemy_count[NA];    // enemy_units_count
+  int16_t income[NP];         // income_per_turn
+  int16_t large_cargo[NS], small_cargo[NS], carriers[NS];
+  uint8_t ut[NP][UT_BYTES];   // units per type: ut[player][land*6+type], ut[player][30+sea*14+type]
+  uint8_t lu[NL][LU_ROW];     // player to move: land units per movement state (reference LandState bytes 4..24)
+  uint8_t su[NS][SU_ROW];     // player to move: sea units per movement state (reference UnitsSea)
+  uint8_t flagged[NA];        // flagged_for_combat
+  uint8_t builds_left[NA];
+  uint8_t money[NP];          // absolute player
+  uint8_t owner[NL];          // absolute owner
+  int8_t factory_hp[NL];
+  uint8_t factory_max[NL];
+  uint8_t bombard_max[NL];
+  int8_t nfact[NP];           // total_factory_count
+  uint8_t factloc[NP][NL];    // factory_locations (ordered lists)
+  uint8_t cur_sea_bombers[NS];  // current_player_sea_unit_types[s][BOMBERS_SEA]: never rotated (src/engine.cpp:3944)
+  uint8_t blockade[NS], edestroyers[NS];
+  uint8_t vm[CAAA_ACTIONS];   // valid_moves (persists across phases and turns, src/engine.cpp:158)
+  uint8_t nvm;
+  uint8_t player;             // player_index as stored (may exceed 4 in caller-supplied states)
+  uint8_t cur;                // player % 5
+  uint8_t canal_state;
+  uint8_t use_selected, selected_action, unlucky;  // expansion mode (src/engine.cpp:156,160,163)
+  uint8_t pad_[1];
+};
+static_assert(sizeof(Game) == 924, "Game layout");
+static_assert((sizeof(Game) / 4) % 2 == 1, "slot stride must be an odd number of words");
+static_assert(offsetof(Game, ut) % 4 == 0 && offsetof(Game, lu) % 4 == 0 && offsetof(Game, flagged) % 4 == 0, "word alignment");
+static_assert((NL * LU_ROW + NS * SU_ROW) % 4 == 0, "per-state counts are cleared word-wise");
+
+struct RunCtx {
+  const DevTables* T;
+  uint32_t seed_lo, seed_hi;
+};
+
+// ---- accessors ----
+CAAA_HD constexpr uint32_t off_lu(int t) { return off_land(t) - 4u; }
+CAAA_HD uint8_t* lu_ptr(Game* g, int l, int t) { return g->lu[l] + off_lu(t); }
+CAAA_HD uint8_t* su_ptr(Game* g, int s, int t) { return g->su[s] + off_sea(t); }
+CAAA_HD uint8_t* utl(Game* g, int pa, int l) { return g->ut[pa] + l * NLT; }
+CAAA_HD uint8_t* uts(Game* g, int pa, int s) { return g->ut[pa] + NL * NLT + s * (NST - 1); }
+CAAA_HD const uint8_t* utl(const Game* g, int pa, int l) { return g->ut[pa] + l * NLT; }
+CAAA_HD const uint8_t* uts(const Game* g, int pa, int s) { return g->ut[pa] + NL * NLT + s * (NST - 1); }
+// current_player_sea_unit_types[s][t]; type 14 (sea bombers) lives outside the per-player vectors
+CAAA_HD uint8_t* cur_sea(Game* g, int s, int t) { return t == BOMBERS_SEA ? &g->cur_sea_bombers[s] : uts(g, g->cur, s) + t; }
+CAAA_HD uint8_t* air_fighters(Game* g, int air) { return air < NL ? lu_ptr(g, air, FIGHTERS) : su_ptr(g, air - NL, FIGHTERS); }
+CAAA_HD uint8_t* air_bombers(Game* g, int air) { return air < NL ? lu_ptr(g, air, BOMBERS_LAND_AIR) : su_ptr(g, air - NL, BOMBERS_SEA); }
+CAAA_HD bool allied(const Game* g, const RunCtx& cx, int pa) { return (cx.T->allied_abs[g->cur] >> pa) & 1; }
+CAAA_HD bool owner_allied(const Game* g, const RunCtx& cx, int land) { return allied(g, cx, g->owner[land]); }
+CAAA_HD int owner_rel(const Game* g, int land) { return (g->owner[land] + NP - g->cur) % NP; }
+
+CAAA_HD bool land_blocked(const Game* g, unsigned flat) { return flat < 25u && ((g->land_blocked >> flat) & 1u); }
+CAAA_HD bool sea_blocked(const Game* g, unsigned flat) { return (g->seasub_blocked >> flat) & 1u; }
+CAAA_HD bool sub_blocked(const Game* g, unsigned flat) { return (g->seasub_blocked >> (16u + flat)) & 1u; }
+
+// skipped_moves as a flat array of 64 one-bit flags (P1 ii): out-of-range reads 0, writes dropped
+CAAA_HD bool skip_get(const Game* g, unsigned a, unsigned b) {
+  const unsigned i = a * 8u + b;
+  return i < 64u && ((g->skipped[i >> 5] >> (i & 31u)) & 1u);
+}
+CAAA_HD void skip_set(Game* g, unsigned a, unsigned b) {
+  const unsigned i = a * 8u + b;
+  if (i < 64u) g->skipped[i >> 5] |= 1u << (i & 31u);
+}
+CAAA_HD uint32_t skip_row(const Game* g, unsigned a) { return a < 8u ? (g->skipped[a >> 2] >> ((a & 3u) * 8u)) & 0xffu : 0u; }
+CAAA_HD void clear_move_history(Game* g) { g->skipped[0] = g->skipped[1] = 0; }  // engine.cpp:1330
+
+constexpr uint32_t W_SEA_BATTLE = 1u << CAAA_PH_SEA_BATTLES, W_LAND_BATTLE = 1u << CAAA_PH_LAND_BATTLES;
+CAAA_HD void flag_combat(Game* g, int air, uint8_t v) {
+  g->flagged[air] = v;
+  if (v) g->work |= air < NL ? W_LAND_BATTLE : W_SEA_BATTLE;
+}
+
+// 4 x u8 dot product (DP4A on the device)
+CAAA_HD uint32_t dot4(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __dp4a(a, b, c);
+#else
+  for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+  return c;
+#endif
+}
+
+// ---- reference layout <-> Game ----
+// Fills everything that the reference keeps in GameState; derived caches are rebuilt by refresh_full_cache().
+CAAA_HD void import_state(Game* g, const uint8_t* src) {
+  const CaaaGameState* st = reinterpret_cast<const CaaaGameState*>(src);
+  const int player = st->player_index, cur = player % NP;
+  g->player = (uint8_t)player;
+  g->cur = (uint8_t)cur;
+  for (int p = 0; p < NP; p++) g->money[(cur + p) % NP] = st->money[p];
+  for (int a = 0; a < NA; a++) {
+    g->builds_left[a] = st->builds_left[a];
+    g->flagged[a] = st->flagged_for_combat[a];
+  }
+  for (int l = 0; l < NL; l++) {
+    const CaaaLandState& ls = st->land_state[l];
+    g->owner[l] = (uint8_t)((ls.owner_idx + cur) % NP);
+    g->factory_hp[l] = ls.factory_hp;
+    g->factory_max[l] = ls.factory_max;
+    g->bombard_max[l] = ls.bombard_max;
+    const uint8_t* u = reinterpret_cast<const uint8_t*>(&ls) + 4;
+    for (int k = 0; k < LU_ROW; k++) g->lu[l][k] = u[k];
+  }
+  for (int s = 0; s < NS; s++) {
+    const uint8_t* u = reinterpret_cast<const uint8_t*>(&st->units_sea[s]);
+    for (int k = 0; k < SU_ROW; k++) g->su[s][k] = u[k];
+  }
+  for (int p = 1; p < NP; p++) {
+    const int pa = (cur + p) % NP;
+    for (int l = 0; l < NL; l++)
+      for (int u = 0; u < NLT; u++) utl(g, pa, l)[u] = st->other_land_units[p - 1][l][u];
+    for (int s = 0; s < NS; s++)
+      for (int u = 0; u < NST - 1; u++) uts(g, pa, s)[u] = st->other_sea_units[p - 1][s][u];
+  }
+  uint32_t sk0 = 0, sk1 = 0;
+  const uint8_t* sm = &st->skipped_moves[0][0];
+  for (int i = 0; i < 32; i++) {
+    sk0 |= (uint32_t)(sm[i] & 1u) << i;
+    sk1 |= (uint32_t)(sm[32 + i] & 1u) << i;
+  }
+  g->skipped[0] = sk0;
+  g->skipped[1] = sk1;
+}
+
+CAAA_HD void export_state(const Game* g, uint8_t* dst) {
+  CaaaGameState* st = reinterpret_cast<CaaaGameState*>(dst);
+  const int cur = g->cur;
+  st->player_index = g->player;
+  for (int p = 0; p < NP; p++) st->money[p] = g->money[(cur + p) % NP];
+  for (int a = 0; a < NA; a++) {
+    st->builds_left[a] = g->builds_left[a];
+    st->flagged_for_combat[a] = g->flagged[a];
+  }
+  for (int l = 0; l < NL; l++) {
+    CaaaLandState& ls = st->land_state[l];
+    ls.owner_idx = (uint8_t)((g->owner[l] + NP - cur) % NP);
+    ls.factory_hp = g->factory_hp[l];
+    ls.factory_max = g->factory_max[l];
+    ls.bombard_max = g->bombard_max[l];
+    uint8_t* u = reinterpret_cast<uint8_t*>(&ls) + 4;
+    for (int k = 0; k < LU_ROW; k++) u[k] = g->lu[l][k];
+  }
+  for (int s = 0; s < NS; s++) {
+    uint8_t* u = reinterpret_cast<uint8_t*>(&st->units_sea[s]);
+    for (int k = 0; k < SU_ROW; k++) u[k] = g->su[s][k];
+  }
+  for (int p = 1; p < NP; p++) {
+    const int pa = (cur + p) % NP;
+    for (int l = 0; l < NL; l++)
+      for (int u = 0; u < NLT; u++) st->other_land_units[p - 1][l][u] = utl(g, pa, l)[u];
+    for (int s = 0; s < NS; s++)
+      for (int u = 0; u < NST - 1; u++) st->other_sea_units[p - 1][s][u] = uts(g, pa, s)[u];
+  }
+  uint8_t* sm = &st->skipped_moves[0][0];
+  for (int i = 0; i < 64; i++) sm[i] = (uint8_t)((g->skipped[i >> 5] >> (i & 31)) & 1u);
+}
+
+// the reference's derived globals in the fixed wire layout of CaaaCacheDump (relative player order)
+CAAA_HD void export_cache(const Game* g, const DevTables* T, CaaaCacheDump* d) {
+  const int cur = g->cur;
+  for (int p = 0; p < 6; p++) {
+    const int pa = (cur + p) % NP;
+    const bool real = p < NP;
+    d->income_per_turn[p] = real ? g->income[pa] : 0;
+    d->total_factory_count[p] = real ? g->nfact[pa] : 0;
+    for (int l = 0; l < NL; l++) {
+      d->factory_locations[p][l] = real ? g->factloc[pa][l] : 0;
+      d->total_player_land_units[p][l] = real ? g->tot_land[pa][l] : 0;
+    }
+    for (int s = 0; s < NS; s++) d->total_player_sea_units[p][s] = real ? g->tot_sea[pa][s] : 0;
+  }
+  for (int s = 0; s < NS; s++) {
+    d->transports_with_large_cargo_space[s] = g->large_cargo[s];
+    d->transports_with_small_cargo_space[s] = g->small_cargo[s];
+    d->allied_carriers[s] = g->carriers[s];
+    d->enemy_blockade_total[s] = g->blockade[s];
+    d->enemy_destroyers_total[s] = g->edestroyers[s];
+  }
+  for (int a = 0; a < NA; a++) d->enemy_units_count[a] = g->enemy_count[a];
+  d->answers_remaining = g->answers_remaining;
+  for (int l = 0; l < NL; l++)
+    for (int u = 0; u < NLT; u++) d->current_player_land_unit_types[l][u] = utl(g, cur, l)[u];
+  for (int s = 0; s < NS; s++) {
+    for (int u = 0; u < NST - 1; u++) d->current_player_sea_unit_types[s][u] = uts(g, cur, s)[u];
+    d->current_player_sea_unit_types[s][BOMBERS_SEA] = g->cur_sea_bombers[s];
+  }
+  for (unsigned i = 0; i < 25; i++) d->is_land_path_blocked[i] = land_blocked(g, i);
+  for (unsigned i = 0; i < 9; i++) {
+    d->is_sea_path_blocked[i] = sea_blocked(g, i);
+    d->is_sub_path_blocked[i] = sub_blocked(g, i);
+  }
+  for (int e = 0; e < 4; e++) d->enemies_0[e] = e < T->n_enemies[cur] ? T->enemies[cur][e] : 0;
+  for (int p = 0; p < NP; p++) d->is_allied_0[p] = (T->allied_mask[cur] >> p) & 1;
+  d->enemies_count_0 = T->n_enemies[cur];
+  d->canal_state = g->canal_state;
+  for (int i = 0; i < CAAA_ACTIONS; i++) d->valid_moves[i] = g->vm[i];
+  d->valid_moves_count = g->nvm;
+  d->pad_[0] = 0;
+}
+
+}  // namespace e2
+}  // namespace caaa

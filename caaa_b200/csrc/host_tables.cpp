@@ -159,7 +159,11 @@ void build_dev_tables(DevTables* out) {
   for (int pi = 0; pi < NP; pi++) {  // refresh_allies (engine.cpp:716-725) for every player to move
     for (int p = 0; p < NP; p++) {
       if (out->t.is_allied[pi][(pi + p) % NP]) out->allied_mask[pi] |= (uint8_t)(1u << p);
-      else out->enemies[pi][out->n_enemies[pi]++] = (uint8_t)p;
+      else {
+        out->enemies_abs[pi][out->n_enemies[pi]] = (uint8_t)((pi + p) % NP);
+        out->enemies[pi][out->n_enemies[pi]++] = (uint8_t)p;
+      }
+      if (out->t.is_allied[pi][p]) out->allied_abs[pi] |= (uint8_t)(1u << p);
     }
   }
 }

@@ -95,6 +95,10 @@ struct DevTables {
   uint8_t n_enemies[NP];
   uint8_t enemies[NP][4];     // relative indices of the enemies, ascending (casualty order depends on it)
   uint8_t pad_[2];
+  // the same lists in absolute player ids (engine2: per-player data is stored in absolute order, never rotated)
+  uint8_t allied_abs[NP];     // bit a set <=> absolute player a is allied with the player to move
+  uint8_t enemies_abs[NP][4]; // absolute ids of the enemies, in the relative order above
+  uint8_t pad2_[3];
 };
 
 // status bits reported per game (0 = clean)

@@ -1,21 +1,21 @@
-// hostsim.cpp -- TEST INFRASTRUCTURE.  Compiles the *device* engine (caaa_b200/csrc/engine.cuh,
-// which is __host__ __device__) with g++ and drives it on the CPU, one slot at a time, through
+// hostsim.cpp -- TEST INFRASTRUCTURE.  Compiles the *device* engine (caaa_b200/csrc/engine2.cuh,
+// which is __host__ __device__) with g++ and drives it on the CPU, one game at a time, through
 // the same C API as the oracle.  It exists so that the kernel's game logic can be checked
 // bit-for-bit against the oracle in the CPU-only test tier (-m "not gpu"), where no GPU is
 // available.  It is never part of the product library, and the product never falls back to it.
 #include <cstring>
 
-#include "../../caaa_b200/csrc/engine.cuh"
+#include "../../caaa_b200/csrc/engine2.cuh"
 #include "../../caaa_b200/csrc/host_tables.h"
 
 using namespace caaa;
+using namespace caaa::e2;
 
 static DevTables g_tables;
-static GameSlot g_slot;
+static Game g_game;
 static RunCtx g_cx;
 static bool g_inited = false;
 static uint64_t g_seed = 0;
-static int g_max_loops = 0;
 
 static void set_ctx() {
   g_cx.T = &g_tables;
@@ -23,10 +23,19 @@ static void set_ctx() {
   g_cx.seed_hi = (uint32_t)(g_seed >> 32);
 }
 
-// random_play_until_terminal, reference src/engine.cpp:4184-4242, on one slot
+static void fill_stats(Game* g, double score, CaaaRolloutStats* st) {
+  st->result = score;
+  st->turns = g->turns;
+  st->decisions = 100000 - g->answers_remaining;
+  st->draws = (int32_t)g->draws;
+  st->final_player = g->player;
+  st->state_hash = hash_live_state(g);
+}
+
+// random_play_until_terminal, reference src/engine.cpp:4184-4242, on one game
 static double play(const void* state670, uint64_t game_id, CaaaRolloutStats* st) {
-  GameSlot* g = &g_slot;
-  std::memcpy(&g->st, state670, CAAA_STATE_BYTES);
+  Game* g = &g_game;
+  import_state(g, (const uint8_t*)state670);
   begin_playout(g, g_cx, game_id);
   double score = evaluate_state(g, g_cx);
   while (score > 0.01 && score < 0.99 && g->turns < 1000) {
@@ -34,19 +43,12 @@ static double play(const void* state670, uint64_t game_id, CaaaRolloutStats* st)
     g->turns++;
     score = evaluate_state(g, g_cx);
   }
-  if (g->st.player_index % 2 == 1) score = 1 - score;
-  if (st) {
-    st->result = score;
-    st->turns = g->turns;
-    st->decisions = 100000 - g->answers_remaining;
-    st->draws = (int32_t)g->draws;
-    st->final_player = g->st.player_index;
-    st->state_hash = hash_live_state(g);
-  }
+  if (g->player % 2 == 1) score = 1 - score;
+  if (st) fill_stats(g, score, st);
   return score;
 }
 
-static void run_until_decision(GameSlot* g) {
+static void run_until_decision(Game* g) {
   for (;;) {
     bool stopped = false;
     for (int ph = 0; ph <= CAAA_PH_BUY_UNITS; ph++)
@@ -60,7 +62,7 @@ extern "C" {
 void caaa_hostsim_init(void) {
   if (g_inited) return;
   build_dev_tables(&g_tables);
-  std::memset(&g_slot, 0, sizeof(g_slot));
+  std::memset(&g_game, 0, sizeof(g_game));
   set_ctx();
   g_inited = true;
 }
@@ -80,85 +82,61 @@ void caaa_hostsim_rollout_many(const void* s, int64_t first, int n, CaaaRolloutS
     if (results) results[i] = r;
   }
 }
-void caaa_hostsim_get_state(void* out) { std::memcpy(out, &g_slot.st, CAAA_STATE_BYTES); }
+void caaa_hostsim_get_state(void* out) { export_state(&g_game, (uint8_t*)out); }
 int caaa_hostsim_stuck(void) {
-  int s = (g_slot.status & CAAA_ERR_SEA_ROUND_CAP) != 0;
-  g_slot.status = 0;
+  int s = (g_game.status & CAAA_ERR_SEA_ROUND_CAP) != 0;
+  g_game.status = 0;
   return s;
 }
 int caaa_hostsim_get_possible_actions(const void* s, uint8_t* actions20) {
-  GameSlot* g = &g_slot;
-  std::memcpy(&g->st, s, CAAA_STATE_BYTES);
-  refresh_full_cache(g, g_cx);
-  g->unlucky = 0;
+  Game* g = &g_game;
+  import_state(g, (const uint8_t*)s);
+  begin_common(g, g_cx);
   g->answers_remaining = 0;
-  g->status = 0;
   run_until_decision(g);
   std::memset(actions20, 0, CAAA_ACTIONS);
   std::memcpy(actions20, g->vm, g->nvm < CAAA_ACTIONS ? g->nvm : CAAA_ACTIONS);
   return g->nvm;
 }
 void caaa_hostsim_apply_action(void* s, uint8_t action) {
-  GameSlot* g = &g_slot;
-  std::memcpy(&g->st, s, CAAA_STATE_BYTES);
-  refresh_full_cache(g, g_cx);
-  g->unlucky = 0;
+  Game* g = &g_game;
+  import_state(g, (const uint8_t*)s);
+  begin_common(g, g_cx);
   g->answers_remaining = 1;
   g->selected_action = action;
   g->use_selected = 1;
-  g->status = 0;
   run_until_decision(g);
-  std::memcpy(s, &g->st, CAAA_STATE_BYTES);
+  export_state(g, (uint8_t*)s);
 }
 int caaa_hostsim_is_terminal(const void* s) {
-  GameSlot tmp = g_slot;
+  // the reference scores a node with the unit tables left behind by the previous call (src/engine.cpp:4314)
+  // but the node's own player index and money (4305-4311)
+  Game tmp = g_game;
   const CaaaGameState* in = (const CaaaGameState*)s;
-  tmp.st.player_index = in->player_index;
-  std::memcpy(tmp.st.money, in->money, NP);
-  double sc = evaluate_state(&tmp, g_cx);
+  const int old_cur = tmp.cur;
+  uint8_t rel_money[NP];
+  for (int p = 0; p < NP; p++) rel_money[p] = in->money[p];
+  tmp.player = in->player_index;
+  // keep the unit tables in the frame they were left in: relative player p stays relative player p
+  Game t2 = tmp;
+  t2.cur = (uint8_t)(in->player_index % NP);
+  for (int p = 0; p < NP; p++) {
+    std::memcpy(t2.ut[(t2.cur + p) % NP], tmp.ut[(old_cur + p) % NP], UT_BYTES);
+    t2.money[(t2.cur + p) % NP] = rel_money[p];
+  }
+  double sc = evaluate_state(&t2, g_cx);
   return sc > 0.99 || sc < 0.01;
 }
 void caaa_hostsim_load_state(const void* s, int64_t game_id) {
-  std::memcpy(&g_slot.st, s, CAAA_STATE_BYTES);
-  begin_playout(&g_slot, g_cx, (uint64_t)game_id);
+  import_state(&g_game, (const uint8_t*)s);
+  begin_playout(&g_game, g_cx, (uint64_t)game_id);
 }
-int caaa_hostsim_run_phase(int ph) { return run_phase<false>(&g_slot, g_cx, ph) ? 1 : 0; }
-double caaa_hostsim_evaluate(void) { return evaluate_state(&g_slot, g_cx); }
-int caaa_hostsim_draws(void) { return (int)g_slot.draws; }
+int caaa_hostsim_run_phase(int ph) { return run_phase<false>(&g_game, g_cx, ph) ? 1 : 0; }
+double caaa_hostsim_evaluate(void) { return evaluate_state(&g_game, g_cx); }
+int caaa_hostsim_draws(void) { return (int)g_game.draws; }
 void caaa_hostsim_get_cache(CaaaCacheDump* d) {
-  GameSlot* g = &g_slot;
   std::memset(d, 0, sizeof(*d));
-  const int pi = pidx(g);
-  for (int p = 0; p < 6; p++) {
-    d->income_per_turn[p] = g->income[p];
-    d->total_factory_count[p] = g->nfact[p];
-    for (int l = 0; l < NL; l++) {
-      d->factory_locations[p][l] = g->factloc[p][l];
-      d->total_player_land_units[p][l] = g->tot_land[p][l];
-    }
-    for (int s = 0; s < NS; s++) d->total_player_sea_units[p][s] = g->tot_sea[p][s];
-  }
-  for (int s = 0; s < NS; s++) {
-    d->transports_with_large_cargo_space[s] = g->large_cargo[s];
-    d->transports_with_small_cargo_space[s] = g->small_cargo[s];
-    d->allied_carriers[s] = g->carriers[s];
-    d->enemy_blockade_total[s] = g->blockade[s];
-    d->enemy_destroyers_total[s] = g->edestroyers[s];
-  }
-  for (int a = 0; a < NA; a++) d->enemy_units_count[a] = g->enemy_count[a];
-  d->answers_remaining = g->answers_remaining;
-  std::memcpy(d->current_player_land_unit_types, g->cur_land, 30);
-  std::memcpy(d->current_player_sea_unit_types, g->cur_sea, 45);
-  std::memcpy(d->is_land_path_blocked, g->land_blocked, 25);
-  std::memcpy(d->is_sea_path_blocked, g->sea_blocked, 9);
-  std::memcpy(d->is_sub_path_blocked, g->sub_blocked, 9);
-  // the team lists are tabulated per player-to-move in this implementation
-  for (int e = 0; e < g_tables.n_enemies[pi]; e++) d->enemies_0[e] = g_tables.enemies[pi][e];
-  for (int p = 0; p < NP; p++) d->is_allied_0[p] = (g_tables.allied_mask[pi] >> p) & 1;
-  d->enemies_count_0 = g_tables.n_enemies[pi];
-  d->canal_state = g->canal_state;
-  std::memcpy(d->valid_moves, g->vm, CAAA_ACTIONS);
-  d->valid_moves_count = g->nvm;
+  export_cache(&g_game, &g_tables, d);
 }
 void caaa_hostsim_get_tables(CaaaTables* t) { *t = g_tables.t; }
 }
@@ -166,7 +144,7 @@ extern "C" void caaa_hostsim_philox(const uint32_t ctr[4], const uint32_t key[2]
   philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
 }
 extern "C" uint8_t caaa_hostsim_stream_byte(uint64_t seed, uint64_t game_id, uint32_t draw_index) {
-  GameSlot g;
+  Game g;
   std::memset(&g, 0, sizeof(g));
   g.game_lo = (uint32_t)game_id;
   g.game_hi = (uint32_t)(game_id >> 32);
@@ -176,29 +154,7 @@ extern "C" uint8_t caaa_hostsim_stream_byte(uint64_t seed, uint64_t game_id, uin
   for (uint32_t d = g.draws; d <= draw_index; d++) b = next_byte(&g, cx);
   return b;
 }
-// playout driven the way the queue scheduler drives it: only phases with work are executed
+// playout driven without the phases >= BUY being special: kept for API compatibility with the tests
 extern "C" void caaa_hostsim_rollout_many_routed(const void* s, int64_t first, int n, CaaaRolloutStats* st) {
-  for (int i = 0; i < n; i++) {
-    GameSlot* g = &g_slot;
-    std::memcpy(&g->st, s, CAAA_STATE_BYTES);
-    begin_playout(g, g_cx, (uint64_t)first + (uint64_t)i);
-    double score = evaluate_state(g, g_cx);
-    while (score > 0.01 && score < 0.99 && g->turns < 1000) {
-      int ph = next_phase_with_work(g, 0);
-      while (ph < CAAA_PH_BUY_UNITS) {
-        run_phase<false>(g, g_cx, ph);
-        ph = next_phase_with_work(g, ph + 1);
-      }
-      for (ph = CAAA_PH_BUY_UNITS; ph < CAAA_PH_COUNT; ph++) run_phase<false>(g, g_cx, ph);
-      g->turns++;
-      score = evaluate_state(g, g_cx);
-    }
-    if (g->st.player_index % 2 == 1) score = 1 - score;
-    st[i].result = score;
-    st[i].turns = g->turns;
-    st[i].decisions = 100000 - g->answers_remaining;
-    st[i].draws = (int32_t)g->draws;
-    st[i].final_player = g->st.player_index;
-    st[i].state_hash = hash_live_state(g);
-  }
+  for (int i = 0; i < n; i++) play(s, (uint64_t)first + (uint64_t)i, st + i);
 }
