@@ -40,7 +40,12 @@ def test_advance_and_midgame(eng):
         c = eng.get_cache()
         for name in ("total_player_land_units", "total_player_sea_units", "enemy_units_count", "income_per_turn",
                      "current_player_sea_unit_types", "valid_moves", "valid_moves_count", "is_land_path_blocked"):
-            assert np.array_equal(c[name], a["caches"][i][name]), (i, name)
+            # row 5 of the per-player caches is rotate_turns' scratch copy (reference src/engine.cpp:3960-3990);
+            # the device engine stores players in absolute order and has no such row
+            got, want = c[name], a["caches"][i][name]
+            if name in ("total_player_land_units", "total_player_sea_units", "income_per_turn"):
+                got, want = got[:5], want[:5]
+            assert np.array_equal(got, want), (i, name)
         st = eng.rollout_many(a["states"][i], int(m["first"]) + i * per_leaf, per_leaf)
         assert np.array_equal(st, m["stats"][i]), i
 
