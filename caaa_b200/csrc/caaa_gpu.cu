@@ -1,12 +1,11 @@
 // caaa_gpu.cu -- sm_100a kernels and the C-ABI of libcaaa_gpu.so (include/caaa_gpu.h).
 //
-// Execution model: one persistent CTA per SM; 192 game slots and the topology tables stay
-// resident in the CTA's 227 KB of shared memory for the whole playout, so the only HBM traffic of a
-// playout is its 670-byte start state in and its result out.  Games are regrouped by phase inside the
-// CTA: every slot carries the id of the next pipeline phase that has work for it, and each warp
-// repeatedly claims up to 32 slots waiting for the same phase (the fullest queue first), so the 32
-// lanes of a warp run the same phase function on 32 games that all have something to do in it.
-// Finished games are replaced from a global ticket counter, which absorbs the long tail of game
+// Execution model: one persistent CTA per SM; 224 games (7 warps x 32 lanes, one game per
+// lane) and the topology tables stay resident in the CTA's 227 KB of shared memory for the whole
+// playout, so the only HBM traffic of a playout is its start state in and its result out.  All 32 lanes
+// of a warp walk the turn pipeline together (engine2.cuh is written so that they stay converged:
+// flat cursor loops, per-game work masks).  Finished games are replaced from a global ticket counter by
+// a warp-cooperative copy of the pre-imported start state, which absorbs the long tail of game
 // lengths.  No tensor cores: the work is branchy uint8 arithmetic.
 #include <cuda_runtime.h>
 
@@ -17,16 +16,20 @@
 #include <string>
 
 #include "../../include/caaa_gpu.h"
-#include "engine.cuh"
+#include "engine2.cuh"
 #include "host_tables.h"
 
 namespace caaa {
+using namespace e2;
 
 constexpr int TABLE_BYTES = (int)((sizeof(DevTables) + 15) / 16 * 16);
-constexpr int ROLLOUT_THREADS = 192;  // slots per CTA: 1328 + 192 * 1180 = 227,888 B of shared memory
-constexpr int SMALL_THREADS = 128;    // non-persistent kernels
+constexpr int GAME_WORDS = (int)(sizeof(Game) / 4);
+constexpr int ROLLOUT_WARPS = 7;                     // 7 x 32 games x 924 B + tables = 208,336 B of shared memory
+constexpr int ROLLOUT_THREADS = ROLLOUT_WARPS * 32;  // one game per thread
+constexpr int SMALL_THREADS = 128;                   // non-persistent kernels
+constexpr unsigned FULL = 0xffffffffu;
 
-extern __shared__ __align__(16) uint8_t smem_raw[];
+// smem_raw (dynamic shared memory, tables first) is declared in game.cuh
 
 __device__ __forceinline__ const DevTables* stage_tables(const DevTables* __restrict__ src) {
   // read-only tables: one copy per CTA in shared memory (divergent indices would serialise in the constant cache)
@@ -36,145 +39,36 @@ __device__ __forceinline__ const DevTables* stage_tables(const DevTables* __rest
   __syncthreads();
   return reinterpret_cast<const DevTables*>(smem_raw);
 }
-__device__ __forceinline__ GameSlot* my_slot() { return reinterpret_cast<GameSlot*>(smem_raw + TABLE_BYTES) + threadIdx.x; }
-
-__device__ __forceinline__ void load_state(GameSlot* g, const uint8_t* __restrict__ src) {
-  const uint16_t* s = reinterpret_cast<const uint16_t*>(src);  // 670 bytes, 2-byte aligned
-  uint16_t* d = reinterpret_cast<uint16_t*>(&g->st);
-#pragma unroll 5
-  for (int i = 0; i < CAAA_STATE_BYTES / 2; i++) d[i] = s[i];
-}
-__device__ __forceinline__ void store_state(const GameSlot* g, uint8_t* __restrict__ dst) {
-  const uint16_t* s = reinterpret_cast<const uint16_t*>(&g->st);
-  uint16_t* d = reinterpret_cast<uint16_t*>(dst);
-#pragma unroll 5
-  for (int i = 0; i < CAAA_STATE_BYTES / 2; i++) d[i] = s[i];
-}
-
-// The fixed pipeline of one player-turn, reference src/engine.cpp:4214-4235.
-template <bool EXPAND>
-__device__ __forceinline__ void play_turn_rollout(GameSlot* g, const RunCtx& cx) {
-  move_fighter_units<EXPAND>(g, cx);
-  move_bomber_units<EXPAND>(g, cx);
-  stage_transport_units<EXPAND>(g, cx);
-  move_land_unit_type<EXPAND>(g, cx, TANKS);
-  move_land_unit_type<EXPAND>(g, cx, ARTILLERY);
-  move_land_unit_type<EXPAND>(g, cx, INFANTRY);
-  move_transport_units<EXPAND>(g, cx);
-  move_subs<EXPAND>(g, cx);
-  move_destroyers_battleships<EXPAND>(g, cx);
-  resolve_sea_battles<EXPAND>(g, cx);
-  unload_transports<EXPAND>(g, cx);
-  resolve_land_battles<EXPAND>(g, cx);
-  move_land_unit_type<EXPAND>(g, cx, AA_GUNS);
-  land_fighter_units<EXPAND>(g, cx);
-  land_bomber_units<EXPAND>(g, cx);
-  buy_units<EXPAND>(g, cx);
-  crash_air_units(g, cx);
-  reset_units_fully(g);
-  collect_money(g, cx);
-  rotate_turns(g, cx);
-}
+__device__ __forceinline__ Game* my_game() { return reinterpret_cast<Game*>(smem_raw + TABLE_BYTES) + threadIdx.x; }
 
 struct RolloutArgs {
   const DevTables* tables;
-  const uint8_t* states;  // n_states x 670 bytes
+  const uint32_t* templates;  // n_states pre-imported Games (prepare_kernel)
+  const double* scores0;      // their first score
   unsigned long long n_games;
   unsigned int rollouts_per_state;
   unsigned long long seed, first_game_id;
   double* results;
-  CaaaRolloutStats* stats;  // optional
+  CaaaRolloutStats* stats;    // optional
   CaaaBatchSummary* summary;  // optional
   unsigned long long* ticket;
-  int debug;
-  int groups;  // barrier sub-groups per CTA (block-synchronous kernel)
 };
 
-template <bool STATS>
-__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const RolloutArgs a) {
-  const DevTables* T = stage_tables(a.tables);
-  GameSlot* g = my_slot();
-  const RunCtx cx{T, (uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-  bool live = false, exhausted = false;
-  unsigned long long gi = 0;
-  double score = 0.0;
-  unsigned long long n_play = 0, n_plies = 0, n_dec = 0, n_draws = 0, n_flag = 0;
-  double sum = 0.0;
-  for (;;) {
-    if (!live && !exhausted) {  // refill at a turn boundary
-      gi = atomicAdd(a.ticket, 1ULL);
-      if (gi < a.n_games) {
-        load_state(g, a.states + (gi / a.rollouts_per_state) * CAAA_STATE_BYTES);
-        begin_playout(g, cx, a.first_game_id + gi);
-        score = evaluate_state(g, cx);
-        live = true;
-      } else {
-        exhausted = true;
-      }
-    }
-    if (!__any_sync(0xffffffffu, live)) break;
-    if (live) {
-      if (score > 0.01 && score < 0.99 && g->turns < 1000) {
-        play_turn_rollout<false>(g, cx);
-        g->turns++;
-        score = evaluate_state(g, cx);
-      } else {  // reference src/engine.cpp:4238-4241
-        const double r = (g->st.player_index % 2 == 1) ? 1.0 - score : score;
-        a.results[gi] = r;
-        const int decisions = 100000 - g->answers_remaining;
-        if (STATS) {
-          CaaaRolloutStats s;
-          s.result = r;
-          s.turns = g->turns;
-          s.decisions = decisions;
-          s.draws = (int32_t)g->draws;
-          s.final_player = g->st.player_index;
-          s.state_hash = hash_live_state(g);
-          a.stats[gi] = s;
-        }
-        n_play++;
-        n_plies += (unsigned long long)g->turns;
-        n_dec += (unsigned long long)decisions;
-        n_draws += g->draws;
-        n_flag += g->status != 0;
-        sum += r;
-        live = false;
-      }
-    }
-  }
-  if (a.summary != nullptr) {  // warp-reduce, then one atomic per warp and counter
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      n_play += __shfl_down_sync(0xffffffffu, n_play, o);
-      n_plies += __shfl_down_sync(0xffffffffu, n_plies, o);
-      n_dec += __shfl_down_sync(0xffffffffu, n_dec, o);
-      n_draws += __shfl_down_sync(0xffffffffu, n_draws, o);
-      n_flag += __shfl_down_sync(0xffffffffu, n_flag, o);
-      sum += __shfl_down_sync(0xffffffffu, sum, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd((unsigned long long*)&a.summary->playouts, n_play);
-      atomicAdd((unsigned long long*)&a.summary->plies, n_plies);
-      atomicAdd((unsigned long long*)&a.summary->decisions, n_dec);
-      atomicAdd((unsigned long long*)&a.summary->draws, n_draws);
-      atomicAdd((unsigned long long*)&a.summary->flagged, n_flag);
-      atomicAdd(&a.summary->sum_result, sum);
-    }
-  }
+// Import every start / leaf state once: reference layout -> Game with all derived caches, ready to be
+// copied into a lane's slot (what random_play_until_terminal does before its loop, src/engine.cpp:4185-4203).
+__global__ void __launch_bounds__(SMALL_THREADS) prepare_kernel(const DevTables* tables, const uint8_t* states, int n,
+                                                                uint32_t* templates, double* scores0) {
+  const DevTables* T = stage_tables(tables);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Game* g = my_game();
+  const RunCtx cx{T, 0u, 0u};
+  import_state(g, states + (size_t)i * CAAA_STATE_BYTES);
+  begin_playout(g, cx, 0);
+  scores0[i] = evaluate_state(g, cx);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(g);
+  for (int k = 0; k < GAME_WORDS; k++) templates[(size_t)i * GAME_WORDS + k] = w[k];
 }
-
-// ------------------------------------------------------------------------------------------------
-// Phase-regrouped persistent rollout kernel.
-// ------------------------------------------------------------------------------------------------
-constexpr int Q_SLOTS = 192;      // game slots per CTA
-constexpr int Q_WARPS = 8;        // more warps than slots/32: batches overlap, queues drain faster
-constexpr int Q_THREADS = Q_WARPS * 32;
-// scheduler states of a slot: 0..14 = waiting for that pipeline phase, then:
-constexpr uint32_t ST_EOT = CAAA_PH_BUY_UNITS;  // 15: purchase + end-of-turn bookkeeping + scoring (always runs)
-constexpr uint32_t ST_START = 16;               // needs a new game from the ticket counter
-constexpr uint32_t ST_BUSY = 30;                // claimed by a lane
-constexpr uint32_t ST_FREE = 31;                // no more games
-constexpr int Q_SMEM = TABLE_BYTES + Q_SLOTS * (int)sizeof(GameSlot) + Q_SLOTS * 4 + 32 * 4;
 
 struct LaneTotals {
   unsigned long long playouts = 0, plies = 0, decisions = 0, draws = 0, flagged = 0;
@@ -182,8 +76,8 @@ struct LaneTotals {
 };
 
 template <bool STATS>
-__device__ __forceinline__ void finish_playout(GameSlot* g, double score, unsigned long long gi, const RolloutArgs& a, LaneTotals& tot) {
-  const double r = (g->st.player_index % 2 == 1) ? 1.0 - score : score;  // reference src/engine.cpp:4238-4241
+__device__ __forceinline__ void finish_playout(Game* g, double score, unsigned long long gi, const RolloutArgs& a, LaneTotals& tot) {
+  const double r = (g->player % 2 == 1) ? 1.0 - score : score;  // reference src/engine.cpp:4238-4241
   a.results[gi] = r;
   const int decisions = 100000 - g->answers_remaining;
   if (STATS) {
@@ -192,7 +86,7 @@ __device__ __forceinline__ void finish_playout(GameSlot* g, double score, unsign
     s.turns = g->turns;
     s.decisions = decisions;
     s.draws = (int32_t)g->draws;
-    s.final_player = g->st.player_index;
+    s.final_player = g->player;
     s.state_hash = hash_live_state(g);
     a.stats[gi] = s;
   }
@@ -204,202 +98,124 @@ __device__ __forceinline__ void finish_playout(GameSlot* g, double score, unsign
   tot.sum += r;
 }
 
-// Block-synchronous variant of the lockstep kernel: a barrier after every phase keeps all warps of the
-// CTA inside the same phase function at the same time, so they share its instructions in the SM's
-// instruction caches (the whole pipeline is ~240 KB of SASS; one phase is 5-30 KB).
-// CTA sub-group barriers (hardware named barriers 1..GROUPS): the warps of one group stay in the same
-// phase function; different groups may drift apart by whole phases, which shortens every barrier wait
-// (max over fewer games) at the price of a few more phases live in the instruction cache.
-__device__ __forceinline__ void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ bool group_or(int id, int count, bool pred) {
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"r"(ROLLOUT_THREADS) : "memory"); }
+__device__ __forceinline__ bool cta_or(bool pred) {
   int out;
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbarrier.red.or.pred p, 1, %2, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(out)
-      : "r"((int)pred), "r"(id), "r"(count)
+      : "r"((int)pred), "r"(ROLLOUT_THREADS)
       : "memory");
   return out != 0;
 }
-#define CAAA_SYNC_PHASE(call)    \
-  do {                           \
-    if (run) { call; }           \
-    group_sync(bar_id, bar_cnt); \
+
+// The fixed pipeline of one player-turn, reference src/engine.cpp:4214-4235.  A phase is only entered by
+// the lanes whose game has work for it (`mw`, voted among the lanes that play a turn this iteration); inside,
+// those lanes stay in lockstep (engine2.cuh).  With SYNC a CTA barrier after every phase keeps all warps of
+// the SM inside the same phase function (they then share its instructions in the SM's instruction caches).
+#define CAAA_PHASE(ph, fn, ...)                                                    \
+  do {                                                                             \
+    if (run) {                                                                     \
+      const unsigned mw = __ballot_sync(mrun, (g->work & W(ph)) != 0);             \
+      if (g->work & W(ph)) fn<false>(g, cx, mw, ##__VA_ARGS__);                    \
+    }                                                                              \
+    if (SYNC) cta_sync();                                                          \
   } while (0)
-template <bool STATS, int LANES, int SLOTS = ROLLOUT_THREADS>
-__global__ void __launch_bounds__(SLOTS / LANES * 32, ROLLOUT_THREADS / SLOTS) rollout_kernel_sync(const RolloutArgs a) {
-  const int n_groups = a.groups;
-  const int warps_per_group = (SLOTS / LANES) / n_groups;
-  const int bar_id = 1 + (int)(threadIdx.x >> 5) / warps_per_group, bar_cnt = warps_per_group * 32;
-  // Only the first LANES lanes of every warp own a game slot.  The kernel is bound by per-warp
-  // latency and by the serialised union of divergent control flow, not by issue slots, so fewer
-  // games per warp (a shorter union) and more warps per SM (more latency hiding) is the better trade.
+
+template <bool STATS, bool SYNC>
+__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const RolloutArgs a) {
   const DevTables* T = stage_tables(a.tables);
-  const int lane = threadIdx.x & 31;
-  const bool owner = lane < LANES;
-  GameSlot* g = reinterpret_cast<GameSlot*>(smem_raw + TABLE_BYTES) + ((threadIdx.x >> 5) * LANES + (owner ? lane : 0));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Game* const warp_games = reinterpret_cast<Game*>(smem_raw + TABLE_BYTES) + warp * 32;
+  Game* const g = warp_games + lane;
   const RunCtx cx{T, (uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-  bool live = false, exhausted = !owner;
+  const bool one_state = a.rollouts_per_state >= a.n_games;
+  bool live = false, exhausted = false;
   unsigned long long gi = 0;
   double score = 0.0;
   LaneTotals tot;
   for (;;) {
-    if (!live && !exhausted) {
-      gi = atomicAdd(a.ticket, 1ULL);
-      if (gi < a.n_games) {
-        load_state(g, a.states + (gi / a.rollouts_per_state) * CAAA_STATE_BYTES);
-        begin_playout(g, cx, a.first_game_id + gi);
-        score = evaluate_state(g, cx);
-        live = true;
-      } else {
-        exhausted = true;
+    // ---- refill idle lanes at a turn boundary: one ticket fetch per warp, then all 32 lanes copy each
+    // new game's 231 words from the pre-imported state (coalesced, converged) ----
+    const unsigned need = __ballot_sync(FULL, !live && !exhausted);
+    if (need) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.ticket, (unsigned long long)__popc(need));
+      base = __shfl_sync(FULL, base, 0);
+      unsigned m = need;
+      while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const unsigned long long gj = base + (unsigned)__popc(need & ((1u << j) - 1u));
+        if (gj < a.n_games) {
+          const unsigned long long sj = one_state ? 0ULL : gj / a.rollouts_per_state;
+          const uint32_t* src = a.templates + sj * GAME_WORDS;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + j);
+#pragma unroll
+          for (int k = 0; k < (GAME_WORDS + 31) / 32; k++)
+            if (k * 32 + lane < GAME_WORDS) dst[k * 32 + lane] = __ldg(src + k * 32 + lane);
+        }
+      }
+      __syncwarp();
+      if ((need >> lane) & 1u) {
+        gi = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+        if (gi < a.n_games) {
+          const unsigned long long id = a.first_game_id + gi;
+          g->game_lo = (uint32_t)id;
+          g->game_hi = (uint32_t)(id >> 32);
+          score = a.scores0[one_state ? 0ULL : gi / a.rollouts_per_state];
+          live = true;
+        } else {
+          exhausted = true;
+        }
       }
     }
-    if (!group_or(bar_id, bar_cnt, live)) break;
+    if (SYNC) {
+      if (!cta_or(live)) break;
+    } else {
+      if (!__any_sync(FULL, live)) break;
+    }
     const bool run = live && score > 0.01 && score < 0.99 && g->turns < 1000;
     if (live && !run) {
       finish_playout<STATS>(g, score, gi, a, tot);
       live = false;
     }
-    CAAA_SYNC_PHASE(move_fighter_units<false>(g, cx));
-    CAAA_SYNC_PHASE(move_bomber_units<false>(g, cx));
-    CAAA_SYNC_PHASE(stage_transport_units<false>(g, cx));
-    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, TANKS));
-    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, ARTILLERY));
-    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, INFANTRY));
-    CAAA_SYNC_PHASE(move_transport_units<false>(g, cx));
-    CAAA_SYNC_PHASE(move_subs<false>(g, cx));
-    CAAA_SYNC_PHASE(move_destroyers_battleships<false>(g, cx));
-    CAAA_SYNC_PHASE(resolve_sea_battles<false>(g, cx));
-    CAAA_SYNC_PHASE(unload_transports<false>(g, cx));
-    CAAA_SYNC_PHASE(resolve_land_battles<false>(g, cx));
-    CAAA_SYNC_PHASE(move_land_unit_type<false>(g, cx, AA_GUNS));
-    CAAA_SYNC_PHASE(land_fighter_units<false>(g, cx));
-    CAAA_SYNC_PHASE(land_bomber_units<false>(g, cx));
-    CAAA_SYNC_PHASE(buy_units<false>(g, cx));
-    CAAA_SYNC_PHASE(crash_air_units(g, cx); reset_units_fully(g); collect_money(g, cx));
-    CAAA_SYNC_PHASE(rotate_turns(g, cx));
+    const unsigned mrun = __ballot_sync(FULL, run);
+    CAAA_PHASE(CAAA_PH_MOVE_FIGHTERS, move_fighter_units);
+    CAAA_PHASE(CAAA_PH_MOVE_BOMBERS, move_bomber_units);
+    CAAA_PHASE(CAAA_PH_STAGE_TRANSPORTS, stage_transport_units);
+    CAAA_PHASE(CAAA_PH_MOVE_TANKS, move_land_unit_type, TANKS, CAAA_PH_MOVE_TANKS);
+    CAAA_PHASE(CAAA_PH_MOVE_ARTILLERY, move_land_unit_type, ARTILLERY, CAAA_PH_MOVE_ARTILLERY);
+    CAAA_PHASE(CAAA_PH_MOVE_INFANTRY, move_land_unit_type, INFANTRY, CAAA_PH_MOVE_INFANTRY);
+    CAAA_PHASE(CAAA_PH_MOVE_TRANSPORTS, move_transport_units);
+    CAAA_PHASE(CAAA_PH_MOVE_SUBS, move_subs);
+    CAAA_PHASE(CAAA_PH_MOVE_SHIPS, move_destroyers_battleships);
+    CAAA_PHASE(CAAA_PH_SEA_BATTLES, resolve_sea_battles);
+    CAAA_PHASE(CAAA_PH_UNLOAD_TRANSPORTS, unload_transports);
+    CAAA_PHASE(CAAA_PH_LAND_BATTLES, resolve_land_battles);
+    CAAA_PHASE(CAAA_PH_MOVE_AA_GUNS, move_land_unit_type, AA_GUNS, CAAA_PH_MOVE_AA_GUNS);
+    CAAA_PHASE(CAAA_PH_LAND_FIGHTERS, land_fighter_units);
+    CAAA_PHASE(CAAA_PH_LAND_BOMBERS, land_bomber_units);
     if (run) {
-      g->turns++;
-      score = evaluate_state(g, cx);
-    }
-  }
-  if (a.summary != nullptr) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      tot.playouts += __shfl_down_sync(0xffffffffu, tot.playouts, o);
-      tot.plies += __shfl_down_sync(0xffffffffu, tot.plies, o);
-      tot.decisions += __shfl_down_sync(0xffffffffu, tot.decisions, o);
-      tot.draws += __shfl_down_sync(0xffffffffu, tot.draws, o);
-      tot.flagged += __shfl_down_sync(0xffffffffu, tot.flagged, o);
-      tot.sum += __shfl_down_sync(0xffffffffu, tot.sum, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd((unsigned long long*)&a.summary->playouts, tot.playouts);
-      atomicAdd((unsigned long long*)&a.summary->plies, tot.plies);
-      atomicAdd((unsigned long long*)&a.summary->decisions, tot.decisions);
-      atomicAdd((unsigned long long*)&a.summary->draws, tot.draws);
-      atomicAdd((unsigned long long*)&a.summary->flagged, tot.flagged);
-      atomicAdd(&a.summary->sum_result, tot.sum);
-    }
-  }
-}
-
-// Run scheduler state `p` on slot g; returns the slot's next scheduler state.
-template <bool STATS>
-__device__ __forceinline__ uint32_t run_item(GameSlot* g, const RunCtx& cx, uint32_t p, const RolloutArgs& a, LaneTotals& tot) {
-  switch (p) {
-    case ST_START: {
-      const unsigned long long gi = atomicAdd(a.ticket, 1ULL);
-      if (gi >= a.n_games) return ST_FREE;
-      load_state(g, a.states + (gi / a.rollouts_per_state) * CAAA_STATE_BYTES);
-      begin_playout(g, cx, a.first_game_id + gi);
-      const double score = evaluate_state(g, cx);
-      if (!(score > 0.01 && score < 0.99)) {  // already terminal: zero turns
-        finish_playout<STATS>(g, score, gi, a, tot);
-        return ST_START;
-      }
-      return (uint32_t)next_phase_with_work(g, 0);
-    }
-    case CAAA_PH_MOVE_FIGHTERS: move_fighter_units<false>(g, cx); break;
-    case CAAA_PH_MOVE_BOMBERS: move_bomber_units<false>(g, cx); break;
-    case CAAA_PH_STAGE_TRANSPORTS: stage_transport_units<false>(g, cx); break;
-    case CAAA_PH_MOVE_TANKS: move_land_unit_type<false>(g, cx, TANKS); break;
-    case CAAA_PH_MOVE_ARTILLERY: move_land_unit_type<false>(g, cx, ARTILLERY); break;
-    case CAAA_PH_MOVE_INFANTRY: move_land_unit_type<false>(g, cx, INFANTRY); break;
-    case CAAA_PH_MOVE_TRANSPORTS: move_transport_units<false>(g, cx); break;
-    case CAAA_PH_MOVE_SUBS: move_subs<false>(g, cx); break;
-    case CAAA_PH_MOVE_SHIPS: move_destroyers_battleships<false>(g, cx); break;
-    case CAAA_PH_SEA_BATTLES: resolve_sea_battles<false>(g, cx); break;
-    case CAAA_PH_UNLOAD_TRANSPORTS: unload_transports<false>(g, cx); break;
-    case CAAA_PH_LAND_BATTLES: resolve_land_battles<false>(g, cx); break;
-    case CAAA_PH_MOVE_AA_GUNS: move_land_unit_type<false>(g, cx, AA_GUNS); break;
-    case CAAA_PH_LAND_FIGHTERS: land_fighter_units<false>(g, cx); break;
-    case CAAA_PH_LAND_BOMBERS: land_bomber_units<false>(g, cx); break;
-    default: {  // ST_EOT: reference src/engine.cpp:4229-4236
-      buy_units<false>(g, cx);
+      buy_units<false>(g, cx, mrun);
       crash_air_units(g, cx);
       reset_units_fully(g);
       collect_money(g, cx);
       rotate_turns(g, cx);
       g->turns++;
-      const double score = evaluate_state(g, cx);
-      if (score > 0.01 && score < 0.99 && g->turns < 1000) return (uint32_t)next_phase_with_work(g, 0);
-      const unsigned long long gi = ((unsigned long long)g->game_hi << 32 | g->game_lo) - a.first_game_id;
-      finish_playout<STATS>(g, score, gi, a, tot);
-      return ST_START;
+      score = evaluate_state(g, cx);
     }
+    if (SYNC) cta_sync();
   }
-  return (uint32_t)next_phase_with_work(g, (int)p + 1);
-}
-
-template <bool STATS>
-__global__ void __launch_bounds__(Q_THREADS, 1) rollout_kernel_regrouped(const RolloutArgs a) {
-  const DevTables* T = stage_tables(a.tables);
-  GameSlot* slots = reinterpret_cast<GameSlot*>(smem_raw + TABLE_BYTES);
-  volatile uint32_t* sstate = reinterpret_cast<volatile uint32_t*>(smem_raw + TABLE_BYTES + Q_SLOTS * sizeof(GameSlot));
-  volatile int* cnt = reinterpret_cast<volatile int*>(sstate + Q_SLOTS);  // pending slots per scheduler state
-  for (int i = threadIdx.x; i < Q_SLOTS; i += blockDim.x) sstate[i] = ST_START;
-  if (threadIdx.x < 32) cnt[threadIdx.x] = threadIdx.x == ST_START ? Q_SLOTS : 0;
-  __syncthreads();
-  const RunCtx cx{T, (uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  LaneTotals tot;
-  for (;;) {
-    // pick the fullest queue (ties: the later state, which is closer to finishing a turn)
-    const int c = lane <= (int)ST_START ? cnt[lane] : 0;
-    const unsigned key = __reduce_max_sync(0xffffffffu, c > 0 ? ((unsigned)c << 5) | (unsigned)lane : 0u);
-    if (key == 0) {
-      if (cnt[ST_FREE] >= Q_SLOTS) break;  // every slot retired
-      __nanosleep(64);
-      continue;
-    }
-    const uint32_t p = key & 31u;
-    int my = -1;
-#pragma unroll 1
-    for (int k = 0; k < Q_SLOTS / 32; k++) {
-      const int s = ((k + warp) % (Q_SLOTS / 32)) * 32 + lane;
-      if (my < 0 && sstate[s] == p && atomicCAS(const_cast<uint32_t*>(&sstate[s]), p, ST_BUSY) == p) my = s;
-    }
-    const int n = __popc(__ballot_sync(0xffffffffu, my >= 0));
-    if (lane == 0 && n > 0) atomicSub(const_cast<int*>(&cnt[p]), n);
-    if (my >= 0) {
-      __threadfence_block();
-      const uint32_t q = run_item<STATS>(slots + my, cx, p, a, tot);
-      __threadfence_block();
-      sstate[my] = q;
-      atomicAdd(const_cast<int*>(&cnt[q]), 1);
-    }
-    __syncwarp();
-  }
-  if (a.summary != nullptr) {
+  if (a.summary != nullptr) {  // warp-reduce, then one atomic per warp and counter
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      tot.playouts += __shfl_down_sync(0xffffffffu, tot.playouts, o);
-      tot.plies += __shfl_down_sync(0xffffffffu, tot.plies, o);
-      tot.decisions += __shfl_down_sync(0xffffffffu, tot.decisions, o);
-      tot.draws += __shfl_down_sync(0xffffffffu, tot.draws, o);
-      tot.flagged += __shfl_down_sync(0xffffffffu, tot.flagged, o);
-      tot.sum += __shfl_down_sync(0xffffffffu, tot.sum, o);
+      tot.playouts += __shfl_down_sync(FULL, tot.playouts, o);
+      tot.plies += __shfl_down_sync(FULL, tot.plies, o);
+      tot.decisions += __shfl_down_sync(FULL, tot.decisions, o);
+      tot.draws += __shfl_down_sync(FULL, tot.draws, o);
+      tot.flagged += __shfl_down_sync(FULL, tot.flagged, o);
+      tot.sum += __shfl_down_sync(FULL, tot.sum, o);
     }
     if (lane == 0) {
       atomicAdd((unsigned long long*)&a.summary->playouts, tot.playouts);
@@ -413,44 +229,12 @@ __global__ void __launch_bounds__(Q_THREADS, 1) rollout_kernel_regrouped(const R
 }
 
 }  // namespace caaa
-#include "stream_kernel.cuh"
+#include "stream.cuh"
 namespace caaa {
 
-// ---- cache dump shared by the advance kernel ----
-__device__ void dump_cache(const GameSlot* g, const DevTables* T, CaaaCacheDump* d) {
-  const int pi = pidx(g);
-  for (int p = 0; p < 6; p++) {
-    d->income_per_turn[p] = g->income[p];
-    d->total_factory_count[p] = g->nfact[p];
-    for (int l = 0; l < NL; l++) {
-      d->factory_locations[p][l] = g->factloc[p][l];
-      d->total_player_land_units[p][l] = g->tot_land[p][l];
-    }
-    for (int s = 0; s < NS; s++) d->total_player_sea_units[p][s] = g->tot_sea[p][s];
-  }
-  for (int s = 0; s < NS; s++) {
-    d->transports_with_large_cargo_space[s] = g->large_cargo[s];
-    d->transports_with_small_cargo_space[s] = g->small_cargo[s];
-    d->allied_carriers[s] = g->carriers[s];
-    d->enemy_blockade_total[s] = g->blockade[s];
-    d->enemy_destroyers_total[s] = g->edestroyers[s];
-  }
-  for (int a = 0; a < NA; a++) d->enemy_units_count[a] = g->enemy_count[a];
-  d->answers_remaining = g->answers_remaining;
-  for (int i = 0; i < 30; i++) (&d->current_player_land_unit_types[0][0])[i] = (&g->cur_land[0][0])[i];
-  for (int i = 0; i < 45; i++) (&d->current_player_sea_unit_types[0][0])[i] = (&g->cur_sea[0][0])[i];
-  for (int i = 0; i < 25; i++) d->is_land_path_blocked[i] = g->land_blocked[i];
-  for (int i = 0; i < 9; i++) {
-    d->is_sea_path_blocked[i] = g->sea_blocked[i];
-    d->is_sub_path_blocked[i] = g->sub_blocked[i];
-  }
-  for (int e = 0; e < 4; e++) d->enemies_0[e] = e < T->n_enemies[pi] ? T->enemies[pi][e] : 0;
-  for (int p = 0; p < NP; p++) d->is_allied_0[p] = (T->allied_mask[pi] >> p) & 1;
-  d->enemies_count_0 = T->n_enemies[pi];
-  d->canal_state = g->canal_state;
-  for (int i = 0; i < CAAA_ACTIONS; i++) d->valid_moves[i] = g->vm[i];
-  d->valid_moves_count = g->nvm;
-  d->pad_[0] = 0;
+__device__ __forceinline__ void play_turn(Game* g, const RunCtx cx, unsigned m) {
+#pragma unroll 1
+  for (int ph = 0; ph < CAAA_PH_COUNT; ph++) run_phase<false>(g, cx, ph, m);
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS) advance_kernel(const DevTables* tables, const uint8_t* states, int n,
@@ -460,13 +244,15 @@ __global__ void __launch_bounds__(SMALL_THREADS) advance_kernel(const DevTables*
   const DevTables* T = stage_tables(tables);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  GameSlot* g = my_slot();
+  const unsigned m = __activemask();  // the lanes of this warp that hold a state walk the pipeline in lockstep
+  Game* g = my_game();
   const RunCtx cx{T, (uint32_t)seed, (uint32_t)(seed >> 32)};
-  load_state(g, states + (size_t)i * CAAA_STATE_BYTES);
+  import_state(g, states + (size_t)i * CAAA_STATE_BYTES);
   begin_playout(g, cx, first_game_id + (unsigned long long)i);
-  for (int t = 0; t < n_turns; t++) play_turn_rollout<false>(g, cx);
-  if (out_states) store_state(g, out_states + (size_t)i * CAAA_STATE_BYTES);
-  if (out_caches) dump_cache(g, T, out_caches + i);
+#pragma unroll 1
+  for (int t = 0; t < n_turns; t++) play_turn(g, cx, m);
+  if (out_states) export_state(g, out_states + (size_t)i * CAAA_STATE_BYTES);
+  if (out_caches) export_cache(g, T, out_caches + i);
   if (out_draws) out_draws[i] = (int32_t)g->draws;
 }
 
@@ -477,14 +263,15 @@ __global__ void __launch_bounds__(SMALL_THREADS) battle_kernel(const DevTables* 
   const DevTables* T = stage_tables(tables);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long draws = 0, flagged = 0, one = 0;
+  const unsigned m = __ballot_sync(FULL, i < n);
   if (i < n) {
-    GameSlot* g = my_slot();
+    Game* g = my_game();
     const RunCtx cx{T, (uint32_t)seed, (uint32_t)(seed >> 32)};
-    load_state(g, states + (size_t)i * CAAA_STATE_BYTES);
+    import_state(g, states + (size_t)i * CAAA_STATE_BYTES);
     begin_playout(g, cx, first_game_id + (unsigned long long)i);
-    resolve_sea_battles<false>(g, cx);
-    resolve_land_battles<false>(g, cx);
-    if (out_states) store_state(g, out_states + (size_t)i * CAAA_STATE_BYTES);
+    resolve_sea_battles<false>(g, cx, m);
+    resolve_land_battles<false>(g, cx, m);
+    if (out_states) export_state(g, out_states + (size_t)i * CAAA_STATE_BYTES);
     if (out_draws) out_draws[i] = (int32_t)g->draws;
     draws = g->draws;
     flagged = g->status != 0;
@@ -493,9 +280,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) battle_kernel(const DevTables* 
   if (summary != nullptr) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      draws += __shfl_down_sync(0xffffffffu, draws, o);
-      flagged += __shfl_down_sync(0xffffffffu, flagged, o);
-      one += __shfl_down_sync(0xffffffffu, one, o);
+      draws += __shfl_down_sync(FULL, draws, o);
+      flagged += __shfl_down_sync(FULL, flagged, o);
+      one += __shfl_down_sync(FULL, one, o);
     }
     if ((threadIdx.x & 31) == 0) {
       atomicAdd((unsigned long long*)&summary->playouts, one);
@@ -506,40 +293,20 @@ __global__ void __launch_bounds__(SMALL_THREADS) battle_kernel(const DevTables* 
 }
 
 // Stop-at-decision mode (reference get_possible_actions / apply_action, src/engine.cpp:4050-4183).
-__device__ __forceinline__ void run_until_decision(GameSlot* g, const RunCtx& cx) {
+__device__ __forceinline__ void run_until_decision(Game* g, const RunCtx cx) {
   for (;;) {
-    if (move_fighter_units<true>(g, cx)) return;
-    if (move_bomber_units<true>(g, cx)) return;
-    if (stage_transport_units<true>(g, cx)) return;
-    if (move_land_unit_type<true>(g, cx, TANKS)) return;
-    if (move_land_unit_type<true>(g, cx, ARTILLERY)) return;
-    if (move_land_unit_type<true>(g, cx, INFANTRY)) return;
-    if (move_transport_units<true>(g, cx)) return;
-    if (move_subs<true>(g, cx)) return;
-    if (move_destroyers_battleships<true>(g, cx)) return;
-    if (resolve_sea_battles<true>(g, cx)) return;
-    if (unload_transports<true>(g, cx)) return;
-    if (resolve_land_battles<true>(g, cx)) return;
-    if (move_land_unit_type<true>(g, cx, AA_GUNS)) return;
-    if (land_fighter_units<true>(g, cx)) return;
-    if (land_bomber_units<true>(g, cx)) return;
-    if (buy_units<true>(g, cx)) return;
-    crash_air_units(g, cx);
-    reset_units_fully(g);
-    collect_money(g, cx);
-    rotate_turns(g, cx);
+    bool stopped = false;
+    for (int ph = 0; ph <= CAAA_PH_BUY_UNITS && !stopped; ph++) stopped = run_phase<true>(g, cx, ph);
+    if (stopped) return;
+    for (int ph = CAAA_PH_CRASH_AIR; ph < CAAA_PH_COUNT; ph++) run_phase<true>(g, cx, ph);
   }
 }
-__device__ __forceinline__ void begin_expansion(GameSlot* g, const RunCtx& cx, int answers, int use_selected, uint8_t action) {
-  refresh_full_cache(g, cx);
-  g->unlucky = 0;
+__device__ __forceinline__ void begin_expansion(Game* g, const RunCtx cx, int answers, int use_selected, uint8_t action) {
+  begin_common(g, cx);
   g->answers_remaining = answers;
   g->use_selected = (uint8_t)use_selected;
   g->selected_action = action;
-  g->draws = 0;
   g->game_lo = g->game_hi = 0;
-  g->turns = 0;
-  g->status = 0;
   for (int i = 0; i < CAAA_ACTIONS; i++) g->vm[i] = 0;
   g->nvm = 0;
 }
@@ -548,9 +315,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) actions_kernel(const DevTables*
   const DevTables* T = stage_tables(tables);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  GameSlot* g = my_slot();
+  Game* g = my_game();
   const RunCtx cx{T, 0u, 0u};
-  load_state(g, leaves + (size_t)i * CAAA_STATE_BYTES);
+  import_state(g, leaves + (size_t)i * CAAA_STATE_BYTES);
   begin_expansion(g, cx, 0, 0, 0);
   run_until_decision(g, cx);
   const int k = g->nvm < CAAA_ACTIONS ? g->nvm : CAAA_ACTIONS;
@@ -565,22 +332,22 @@ __global__ void __launch_bounds__(SMALL_THREADS) apply_kernel(const DevTables* t
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = idx / CAAA_ACTIONS, k = idx % CAAA_ACTIONS;
   if (i >= n || k >= n_actions[i]) return;
-  GameSlot* g = my_slot();
+  Game* g = my_game();
   const RunCtx cx{T, 0u, 0u};
-  load_state(g, leaves + (size_t)i * CAAA_STATE_BYTES);
+  import_state(g, leaves + (size_t)i * CAAA_STATE_BYTES);
   begin_expansion(g, cx, 1, 1, actions[(size_t)i * CAAA_ACTIONS + k]);
   run_until_decision(g, cx);
-  store_state(g, children + (size_t)idx * CAAA_STATE_BYTES);
+  export_state(g, children + (size_t)idx * CAAA_STATE_BYTES);
   if (status && g->status) atomicOr(&status[i], 1u << k);  // bit k: child k tripped a guard
 }
 __global__ void __launch_bounds__(SMALL_THREADS) evaluate_kernel(const DevTables* tables, const uint8_t* states, int n, double* scores) {
   const DevTables* T = stage_tables(tables);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  GameSlot* g = my_slot();
+  Game* g = my_game();
   const RunCtx cx{T, 0u, 0u};
-  load_state(g, states + (size_t)i * CAAA_STATE_BYTES);
-  refresh_full_cache(g, cx);
+  import_state(g, states + (size_t)i * CAAA_STATE_BYTES);
+  begin_common(g, cx);
   scores[i] = evaluate_state(g, cx);
 }
 
@@ -604,17 +371,17 @@ struct Context {
   size_t aux_cap = 0;
   void* d_aux2 = nullptr;
   size_t aux2_cap = 0;
+  void* d_templates = nullptr;  // pre-imported start states + their first scores
+  size_t templates_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long seed = 0, next_game_id = 0;
-  bool lockstep = false, sync = true, regrouped = false, streaming = false;
-  int lanes = 8, ctas_per_sm = 1, groups = 1;
-  // device-wide phase queues + game pool of the streaming kernel (allocated on first use)
-  PhaseQueues* d_queues = nullptr;
-  unsigned long long* d_cells = nullptr;
-  PoolSlot* d_pool = nullptr;
-  unsigned pool_size = 0;
-  int pool_mult = 2;
+  bool sync_phases = false;  // CAAA_SYNC=1: CTA barrier after every phase (A/B knob)
+  bool streaming = true;     // CAAA_ROLLOUT_KERNEL=lockstep selects the walk-the-pipeline kernel instead
+  int pool_mult = 3;         // pool entries per shared-memory slot (CAAA_POOL_MULT)
+  int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
+  void* d_pool = nullptr;    // per-SM game pools of the phase-regrouped kernel
+  size_t pool_cap = 0;
 };
 static Context g_ctx;
 static std::string g_err;
@@ -642,17 +409,33 @@ static int grow(void** p, size_t* cap, size_t need) {
   *cap = need;
   return CAAA_OK;
 }
-static int small_smem() { return TABLE_BYTES + SMALL_THREADS * (int)sizeof(GameSlot); }
-static int rollout_smem() { return TABLE_BYTES + ROLLOUT_THREADS * (int)sizeof(GameSlot); }
+static int small_smem() { return TABLE_BYTES + SMALL_THREADS * (int)sizeof(Game); }
+static int rollout_smem() { return TABLE_BYTES + ROLLOUT_THREADS * (int)sizeof(Game); }
 
-static int launch_rollout(const void* d_states, unsigned long long n_games, unsigned rollouts_per_state,
-                          unsigned long long seed, unsigned long long first_game_id, double* d_results,
-                          CaaaRolloutStats* d_stats, CaaaBatchSummary* d_summary, cudaStream_t stream) {
+static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_per_state, unsigned long long seed,
+                          unsigned long long first_game_id, double* d_results, CaaaRolloutStats* d_stats,
+                          CaaaBatchSummary* d_summary, cudaStream_t stream) {
   Context& c = g_ctx;
+  const unsigned long long n_games = (unsigned long long)n_states * rollouts_per_state;
+  const size_t tmpl_bytes = (size_t)n_states * sizeof(Game);
+  int rc = grow(&c.d_templates, &c.templates_cap, tmpl_bytes + (size_t)n_states * sizeof(double));
+  if (rc != CAAA_OK) return rc;
+  uint32_t* d_tmpl = (uint32_t*)c.d_templates;
+  double* d_scores0 = (double*)((uint8_t*)c.d_templates + (tmpl_bytes + 7) / 8 * 8);
+  if ((tmpl_bytes + 7) / 8 * 8 + (size_t)n_states * sizeof(double) > c.templates_cap) {
+    rc = grow(&c.d_templates, &c.templates_cap, (tmpl_bytes + 7) / 8 * 8 + (size_t)n_states * sizeof(double));
+    if (rc != CAAA_OK) return rc;
+    d_tmpl = (uint32_t*)c.d_templates;
+    d_scores0 = (double*)((uint8_t*)c.d_templates + (tmpl_bytes + 7) / 8 * 8);
+  }
+  prepare_kernel<<<(n_states + SMALL_THREADS - 1) / SMALL_THREADS, SMALL_THREADS, small_smem(), stream>>>(
+      c.d_tables, (const uint8_t*)d_states, n_states, d_tmpl, d_scores0);
+  CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned long long), stream));
   RolloutArgs a;
   a.tables = c.d_tables;
-  a.states = (const uint8_t*)d_states;
+  a.templates = d_tmpl;
+  a.scores0 = d_scores0;
   a.n_games = n_games;
   a.rollouts_per_state = rollouts_per_state;
   a.seed = seed;
@@ -661,84 +444,42 @@ static int launch_rollout(const void* d_states, unsigned long long n_games, unsi
   a.stats = d_stats;
   a.summary = d_summary;
   a.ticket = c.d_ticket;
-  a.debug = std::getenv("CAAA_DEBUG") != nullptr;
-  a.groups = c.groups;
+  const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
+  const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
   if (c.streaming) {
-    const unsigned long long want = (n_games + STREAM_SLOTS - 1) / STREAM_SLOTS;
-    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
-    const unsigned need = (unsigned)c.sm_count * STREAM_SLOTS * (unsigned)c.pool_mult;
-    if (c.d_pool == nullptr || c.pool_size < need) {
-      if (c.d_pool) { cudaFree(c.d_pool); cudaFree(c.d_cells); cudaFree(c.d_queues); c.d_pool = nullptr; }
-      unsigned cap = 1;
-      while (cap < need) cap <<= 1;
-      CUDA_TRY(cudaMalloc(&c.d_pool, (size_t)need * sizeof(PoolSlot)));
-      CUDA_TRY(cudaMalloc(&c.d_cells, (size_t)NQ * cap * sizeof(unsigned long long)));
-      CUDA_TRY(cudaMalloc(&c.d_queues, sizeof(PhaseQueues)));
-      CUDA_TRY(cudaMemset(c.d_cells, 0, (size_t)NQ * cap * sizeof(unsigned long long)));
-      PhaseQueues h;
-      std::memset(&h, 0, sizeof(h));
-      h.capacity = cap;
-      h.pool_size = need;
-      h.cells = c.d_cells;
-      h.pool = c.d_pool;
-      CUDA_TRY(cudaMemcpy(c.d_queues, &h, sizeof(h), cudaMemcpyHostToDevice));
-      c.pool_size = need;
+    const size_t need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game);
+    int rc2 = grow(&c.d_pool, &c.pool_cap, need + sizeof(StreamDbg));
+    if (rc2 != CAAA_OK) return rc2;
+    StreamDbg* d_dbg = nullptr;
+    if (std::getenv("CAAA_DEBUG") != nullptr) {
+      d_dbg = (StreamDbg*)((uint8_t*)c.d_pool + need);
+      CUDA_TRY(cudaMemsetAsync(d_dbg, 0, sizeof(StreamDbg), stream));
     }
-    // queue positions keep counting across launches (cells are tagged with them); only the per-launch counters reset
-    queues_reset_kernel<<<1, 32, 0, stream>>>(c.d_queues);
-    // a launch with fewer CTAs than the pool was sized for simply uses fewer pool entries
-    if (d_stats)
-      rollout_kernel_stream<true><<<grid, STREAM_THREADS + 32, rollout_smem(), stream>>>(a, c.d_queues);
-    else
-      rollout_kernel_stream<false><<<grid, STREAM_THREADS + 32, rollout_smem(), stream>>>(a, c.d_queues);
-    if (a.debug) {
-      PhaseQueues h;
-      cudaStreamSynchronize(stream);
-      cudaMemcpy(&h, c.d_queues, sizeof(h), cudaMemcpyDeviceToHost);
-      std::fprintf(stderr, "stream dbg: items %llu empty_polls %llu ticket_wait_polls %llu switches %llu busy_frac %.3f aborted %d\n",
-                   h.dbg[0], h.dbg[1], h.dbg[2], h.dbg[3], h.dbg[5] ? (double)h.dbg[4] / (double)h.dbg[5] : 0.0, h.aborted);
-    }
-  } else if (c.sync) {
-    const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
-    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
-#define CAAA_LAUNCH_SYNC(L)                                                                             \
-  do {                                                                                                 \
-    if (d_stats)                                                                                       \
-      rollout_kernel_sync<true, L><<<grid, ROLLOUT_THREADS / L * 32, rollout_smem(), stream>>>(a);     \
-    else                                                                                               \
-      rollout_kernel_sync<false, L><<<grid, ROLLOUT_THREADS / L * 32, rollout_smem(), stream>>>(a);    \
+#define CAAA_LAUNCH_STREAM(L)                                                                                                        \
+  do {                                                                                                                              \
+    if (d_stats)                                                                                                                    \
+      rollout_kernel_stream<true, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_dbg);  \
+    else                                                                                                                            \
+      rollout_kernel_stream<false, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_dbg); \
   } while (0)
-    if (c.ctas_per_sm > 1) {  // several smaller CTAs per SM: one CTA's barrier waits overlap another's work
-      const int slots = c.ctas_per_sm == 2 ? 96 : 64;
-      const unsigned long long want2 = (n_games + slots - 1) / slots;
-      const unsigned long long cap = (unsigned long long)c.sm_count * c.ctas_per_sm;
-      const int grid2 = (int)(want2 < cap ? want2 : cap);
-      const int smem2 = TABLE_BYTES + slots * (int)sizeof(GameSlot);
-      if (c.ctas_per_sm == 2) {
-        if (d_stats) rollout_kernel_sync<true, 8, 96><<<grid2, 96 / 8 * 32, smem2, stream>>>(a);
-        else rollout_kernel_sync<false, 8, 96><<<grid2, 96 / 8 * 32, smem2, stream>>>(a);
-      } else {
-        if (d_stats) rollout_kernel_sync<true, 8, 64><<<grid2, 64 / 8 * 32, smem2, stream>>>(a);
-        else rollout_kernel_sync<false, 8, 64><<<grid2, 64 / 8 * 32, smem2, stream>>>(a);
-      }
-    } else if (c.lanes == 32) CAAA_LAUNCH_SYNC(32);
-    else if (c.lanes == 16) CAAA_LAUNCH_SYNC(16);
-    else if (c.lanes == 6) CAAA_LAUNCH_SYNC(6);
-    else CAAA_LAUNCH_SYNC(8);
-  } else if (c.lockstep) {  // first-generation kernel, kept for A/B measurements (CAAA_ROLLOUT_KERNEL=lockstep)
-    const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
-    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
-    if (d_stats)
-      rollout_kernel<true><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
-    else
-      rollout_kernel<false><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
+    if (c.lanes == 32) CAAA_LAUNCH_STREAM(32);
+    else if (c.lanes == 8) CAAA_LAUNCH_STREAM(8);
+    else CAAA_LAUNCH_STREAM(16);
+    if (d_dbg != nullptr) {
+      StreamDbg h;
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(&h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      const double tt = (double)(h.t[0] + h.t[1] + h.t[2] + h.t[3] + h.t[4]);
+      std::fprintf(stderr, "stream dbg: batches %llu items/batch %.1f  idle+claim %.3f in %.3f compute %.3f restart %.3f out %.3f  Mcyc/warp %.1f\n",
+                   h.batches, h.batches ? (double)h.items / (double)h.batches : 0.0, h.t[0] / tt, h.t[1] / tt, h.t[2] / tt, h.t[3] / tt,
+                   h.t[4] / tt, tt / (grid * (STREAM_SLOTS / c.lanes)) / 1e6);
+    }
+  } else if (c.sync_phases) {
+    if (d_stats) rollout_kernel<true, true><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
+    else rollout_kernel<false, true><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
   } else {
-    const unsigned long long want = (n_games + Q_SLOTS - 1) / Q_SLOTS;
-    const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
-    if (d_stats)
-      rollout_kernel_regrouped<true><<<grid, Q_THREADS, Q_SMEM, stream>>>(a);
-    else
-      rollout_kernel_regrouped<false><<<grid, Q_THREADS, Q_SMEM, stream>>>(a);
+    if (d_stats) rollout_kernel<true, false><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
+    else rollout_kernel<false, false><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);
   }
   CUDA_TRY(cudaGetLastError());
   return CAAA_OK;
@@ -774,39 +515,28 @@ int caaa_gpu_init(int device) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&c.ev0));
   CUDA_TRY(cudaEventCreate(&c.ev1));
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_regrouped<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_regrouped<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
-  {
-    const char* k = std::getenv("CAAA_ROLLOUT_KERNEL");
-    c.lockstep = k != nullptr && std::strcmp(k, "lockstep") == 0;
-    c.regrouped = k != nullptr && std::strcmp(k, "regrouped") == 0;
-    c.streaming = k != nullptr && std::strcmp(k, "stream") == 0;
-    c.sync = !c.lockstep && !c.regrouped && !c.streaming;  // default: block-synchronous phases
-    const char* pm = std::getenv("CAAA_POOL_MULT");
-    c.pool_mult = pm ? std::atoi(pm) : 2;
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    const char* l = std::getenv("CAAA_LANES");
-    c.lanes = l ? std::atoi(l) : 8;
-    const char* gp = std::getenv("CAAA_GROUPS");
-    c.groups = gp ? std::atoi(gp) : 1;
-    const char* cp = std::getenv("CAAA_CTAS_PER_SM");
-    c.ctas_per_sm = cp ? std::atoi(cp) : 1;
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 8, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 96 * (int)sizeof(GameSlot)));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 8, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 96 * (int)sizeof(GameSlot)));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 64 * (int)sizeof(GameSlot)));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 8, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TABLE_BYTES + 64 * (int)sizeof(GameSlot)));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<true, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-    CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_sync<false, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
-  }
+  const char* sy = std::getenv("CAAA_SYNC");
+  c.sync_phases = sy != nullptr && std::atoi(sy) != 0;
+  const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
+  c.streaming = !(rk != nullptr && std::strcmp(rk, "lockstep") == 0);
+  const char* pm = std::getenv("CAAA_POOL_MULT");
+  c.pool_mult = pm ? std::atoi(pm) : 3;
+  if (c.pool_mult < 1) c.pool_mult = 1;
+  if (c.pool_mult > MAX_POOL_MULT) c.pool_mult = MAX_POOL_MULT;
+  const char* ln = std::getenv("CAAA_LANES");
+  c.lanes = ln ? std::atoi(ln) : 16;
+  if (c.lanes != 8 && c.lanes != 32) c.lanes = 16;
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+  CUDA_TRY(cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(actions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
@@ -827,6 +557,8 @@ int caaa_gpu_shutdown(void) {
   if (c.d_out) cudaFree(c.d_out);
   if (c.d_aux) cudaFree(c.d_aux);
   if (c.d_aux2) cudaFree(c.d_aux2);
+  if (c.d_templates) cudaFree(c.d_templates);
+  if (c.d_pool) cudaFree(c.d_pool);
   cudaEventDestroy(c.ev0);
   cudaEventDestroy(c.ev1);
   cudaStreamDestroy(c.stream);
@@ -858,8 +590,7 @@ int caaa_gpu_rollout_batch_device(const void* d_states, int n_states, int rollou
                                   CaaaBatchSummary* d_summary, void* cuda_stream) {
   if (!g_ctx.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!d_states || !d_results || n_states <= 0 || rollouts_per_state <= 0) return fail(CAAA_E_ARG, "bad rollout batch arguments");
-  return launch_rollout(d_states, (unsigned long long)n_states * (unsigned long long)rollouts_per_state,
-                        (unsigned)rollouts_per_state, seed, first_game_id, d_results, d_stats, d_summary,
+  return launch_rollout(d_states, n_states, (unsigned)rollouts_per_state, seed, first_game_id, d_results, d_stats, d_summary,
                         (cudaStream_t)cuda_stream);
 }
 
@@ -877,7 +608,7 @@ int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollou
   CUDA_TRY(cudaMemcpyAsync(c.d_in, states, in_bytes, cudaMemcpyHostToDevice, c.stream));
   CUDA_TRY(cudaMemsetAsync(c.d_summary, 0, sizeof(CaaaBatchSummary), c.stream));
   CUDA_TRY(cudaEventRecord(c.ev0, c.stream));
-  rc = launch_rollout(c.d_in, n_games, (unsigned)rollouts_per_state, seed, first_game_id, (double*)c.d_out,
+  rc = launch_rollout(c.d_in, n_states, (unsigned)rollouts_per_state, seed, first_game_id, (double*)c.d_out,
                       stats ? (CaaaRolloutStats*)c.d_aux : nullptr, c.d_summary, c.stream);
   if (rc != CAAA_OK) return rc;
   CUDA_TRY(cudaEventRecord(c.ev1, c.stream));

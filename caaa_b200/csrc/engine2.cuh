@@ -25,10 +25,10 @@
 namespace caaa {
 namespace e2 {
 
-constexpr uint32_t W(int ph) { return 1u << ph; }
+CAAA_HD constexpr uint32_t W(int ph) { return 1u << ph; }
 constexpr uint32_t W_ALL_MOVES = 0x7fffu;  // phases 0..14
 
-CAAA_HD_NOINLINE uint8_t next_byte(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE uint8_t next_byte(Game* g, const RunCtx cx) {
   const uint32_t d = g->draws++;
   const uint32_t k = d & 15u;
   if (k == 0) philox4x32_10(d >> 4, g->game_lo, g->game_hi, 0u, cx.seed_lo, cx.seed_hi, g->rng);
@@ -36,24 +36,28 @@ CAAA_HD_NOINLINE uint8_t next_byte(Game* g, const RunCtx& cx) {
 }
 
 // ---- cache refresh, engine.cpp:642-814 ----
-CAAA_HD_NOINLINE void refresh_eot_cache(Game* g, const RunCtx& cx) {  // 653-660 (refresh_allies is tabulated)
-  const CaaaTables& t = cx.T->t;
-  const int cur = g->cur, ne = cx.T->n_enemies[cur];
-  const uint8_t* en = cx.T->enemies_abs[cur];
+CAAA_HD_NOINLINE void refresh_eot_cache(Game* g, const RunCtx cx) {  // 653-660 (refresh_allies is tabulated)
+  const CaaaTables& t = CAAA_TAB(cx)->t;
+  const int cur = g->cur, ne = CAAA_TAB(cx)->n_enemies[cur];
+  const uint8_t* en = CAAA_TAB(cx)->enemies_abs[cur];
   uint32_t cs = 0;  // refresh_canals 726-733 (the canal-specific table copies are read through canal_state)
 #pragma unroll
   for (int k = 0; k < CAAA_CANALS; k++)
     if (owner_allied(g, cx, t.canal_lands[k][0]) && owner_allied(g, cx, t.canal_lands[k][1])) cs += 1u << k;
   g->canal_state = (uint8_t)cs;
+#pragma unroll 1
   for (int l = 0; l < NL; l++) {  // refresh_enemy_armies 752-760
     int n = 0;
+#pragma unroll 1
     for (int e = 0; e < ne; e++) n += g->tot_land[en[e]][l];
     g->enemy_count[l] = (int16_t)n;
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {  // refresh_fleets 761-784
     const uint8_t* mine = uts(g, cur, s);
     int carriers = 0, ecount = 0;
     uint32_t edest = 0, block = 0;
+#pragma unroll 1
     for (int pa = 0; pa < NP; pa++) {
       const uint8_t* su = uts(g, pa, s);
       if (allied(g, cx, pa)) {
@@ -72,7 +76,9 @@ CAAA_HD_NOINLINE void refresh_eot_cache(Game* g, const RunCtx& cx) {  // 653-660
     g->small_cargo[s] = (int16_t)(mine[TRANS_EMPTY] + mine[TRANS_1I] + mine[TRANS_1A] + mine[TRANS_1T]);
   }
   uint32_t lb = g->land_blocked;  // refresh_*_path_blocked 785-814: only the listed entries are ever written
+#pragma unroll 1
   for (int s = 0; s < NL; s++)
+#pragma unroll 1
     for (int i = 0; i < t.lands_within_2_count[s]; i++) {
       const int d = t.lands_within_2[s][i];
       const int n1 = t.land_path[s][d], n2 = t.land_path_alt[s][d];
@@ -82,7 +88,9 @@ CAAA_HD_NOINLINE void refresh_eot_cache(Game* g, const RunCtx& cx) {  // 653-660
     }
   g->land_blocked = lb;
   uint32_t sb = g->seasub_blocked;
+#pragma unroll 1
   for (int s = 0; s < NS; s++)
+#pragma unroll 1
     for (int i = 0; i < t.seas_within_2_count[cs][s]; i++) {
       const int d = t.seas_within_2[cs][s][i];
       const int n1 = t.sea_path[cs][s][d], n2 = t.sea_path_alt[cs][s][d];
@@ -93,39 +101,50 @@ CAAA_HD_NOINLINE void refresh_eot_cache(Game* g, const RunCtx& cx) {  // 653-660
   g->seasub_blocked = sb;
 }
 
-CAAA_HD_NOINLINE void refresh_full_cache(Game* g, const RunCtx& cx) {  // 642-652, 661-715
+CAAA_HD_NOINLINE void refresh_full_cache(Game* g, const RunCtx cx) {  // 642-652, 661-715
   const int cur = g->cur;
+#pragma unroll 1
   for (int p = 0; p < NP; p++) {
     g->income[p] = 0;
     g->nfact[p] = 0;
   }
+#pragma unroll 1
   for (int l = 0; l < NL; l++) {
     const int owner = g->owner[l];
     if (g->factory_max[l] > 0) g->factloc[owner][g->nfact[owner]++] = (uint8_t)l;
-    g->income[owner] = (int16_t)(g->income[owner] + cx.T->t.land_value[l]);
+    g->income[owner] = (int16_t)(g->income[owner] + CAAA_TAB(cx)->t.land_value[l]);
+#pragma unroll 1
     for (int u = 0; u < NLT; u++) {
       const uint8_t* s = lu_ptr(g, l, u);
       uint32_t n = 0;
+#pragma unroll 1
       for (int k = 0; k < (int)states_land(u); k++) n += s[k];
       utl(g, cur, l)[u] = (uint8_t)n;
     }
+#pragma unroll 1
     for (int pa = 0; pa < NP; pa++) {
       const uint8_t* r = utl(g, pa, l);
       int n = 0;
+#pragma unroll 1
       for (int u = 0; u < NLT; u++) n += r[u];
       g->tot_land[pa][l] = (int16_t)n;
     }
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
+#pragma unroll 1
     for (int u = 0; u < NST; u++) {
       const uint8_t* q = su_ptr(g, s, u);
       uint32_t n = 0;
+#pragma unroll 1
       for (int k = 0; k < (int)states_sea(u); k++) n += q[k];
       *cur_sea(g, s, u) = (uint8_t)n;
     }
+#pragma unroll 1
     for (int pa = 0; pa < NP; pa++) {
       const uint8_t* r = uts(g, pa, s);
       int n = 0;
+#pragma unroll 1
       for (int u = 0; u < NST - 1; u++) n += r[u];
       g->tot_sea[pa][s] = (int16_t)n;
     }
@@ -135,22 +154,23 @@ CAAA_HD_NOINLINE void refresh_full_cache(Game* g, const RunCtx& cx) {  // 642-65
 
 // ---- decisions and dice ----
 template <bool EXPAND>
-CAAA_HD uint8_t ai_input(Game* g, const RunCtx& cx) {  // getAIInput 1291-1297
+CAAA_HD uint8_t ai_input(Game* g, const RunCtx cx) {  // getAIInput 1291-1297
   g->answers_remaining--;
   if (EXPAND && g->use_selected) return g->selected_action;
   return g->vm[next_byte(g, cx) % g->nvm];
 }
-CAAA_HD bool unlucky_team(const Game* g, const RunCtx& cx) { return cx.T->t.is_allied[g->cur][g->unlucky % NP] != 0; }
-CAAA_HD uint32_t attacker_hits(Game* g, const RunCtx& cx, int dmg) {  // 2552-2565
+CAAA_HD bool unlucky_team(const Game* g, const RunCtx cx) { return CAAA_TAB(cx)->t.is_allied[g->cur][g->unlucky % NP] != 0; }
+CAAA_HD uint32_t attacker_hits(Game* g, const RunCtx cx, int dmg) {  // 2552-2565
   if (g->answers_remaining < 2) return (uint8_t)(unlucky_team(g, cx) ? dmg / 6 : dmg / 6 + (1 < dmg % 6 ? 1 : 0));
   return (uint8_t)(dmg / 6 + ((int)(next_byte(g, cx) % 6) < dmg % 6 ? 1 : 0));
 }
-CAAA_HD uint32_t defender_hits(Game* g, const RunCtx& cx, int dmg) {  // 2567-2580
+CAAA_HD uint32_t defender_hits(Game* g, const RunCtx cx, int dmg) {  // 2567-2580
   if (g->answers_remaining < 2) return (uint8_t)(unlucky_team(g, cx) ? dmg / 6 + (1 < dmg % 6 ? 1 : 0) : dmg / 6);
   return (uint8_t)(dmg / 6 + ((int)(next_byte(g, cx) % 6) < dmg % 6 ? 1 : 0));
 }
 
 CAAA_HD void update_move_history_4air(Game* g, uint32_t src, uint32_t dst) {  // 1300-1328: starts one past the list
+#pragma unroll 1
   for (;;) {
     const uint32_t va = g->nvm < CAAA_ACTIONS ? g->vm[g->nvm] : 0u;
     if (va == dst) break;
@@ -162,9 +182,11 @@ CAAA_HD void update_move_history_4air(Game* g, uint32_t src, uint32_t dst) {  //
 }
 
 CAAA_HD_NOINLINE bool load_transport(Game* g, int ut, int src_land, int dst_sea, int land_state) {  // 1397-1443
+#pragma unroll 1
   for (int tt = weight_land(ut) > 2 ? TRANS_1I : TRANS_1T; tt >= TRANS_EMPTY; tt--) {
     uint8_t* arr = su_ptr(g, dst_sea, tt);
     const int unl = unloading_sea(tt);
+#pragma unroll 1
     for (int ts = (int)states_sea(tt) - (int)staging_sea(tt); ts >= unl; ts--) {
       if (arr[ts] == 0) continue;
       const int ntt = load_result(ut, tt);
@@ -186,16 +208,18 @@ CAAA_HD_NOINLINE bool load_transport(Game* g, int ut, int src_land, int dst_sea,
   return false;
 }
 
-CAAA_HD_NOINLINE void add_valid_land_moves(Game* g, const RunCtx& cx, int src, int moves, int ut) {  // 1445-1516
-  const CaaaTables& t = cx.T->t;
+CAAA_HD_NOINLINE void add_valid_land_moves(Game* g, const RunCtx cx, int src, int moves, int ut) {  // 1445-1516
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   uint32_t n = g->nvm;
   if (moves == 2) {
+#pragma unroll 1
     for (int i = 0; i < t.lands_within_2_count[src]; i++) {
       const int d = t.lands_within_2[src][i];
       if (skip_get(g, src, d)) continue;
       if (t.land_dist[src][d] == 2 && land_blocked(g, src * NL + d)) continue;
       g->vm[n++] = (uint8_t)d;
     }
+#pragma unroll 1
     for (int i = 0; i < t.load_within_2_count[src]; i++) {
       const int ds = t.load_within_2[src][i];
       if (g->large_cargo[ds] == 0) continue;
@@ -209,6 +233,7 @@ CAAA_HD_NOINLINE void add_valid_land_moves(Game* g, const RunCtx& cx, int src, i
     return;
   }
   const bool non_combat = ut == AA_GUNS, unloadable = weight_land(ut) > 5, heavy = weight_land(ut) > 2;
+#pragma unroll 1
   for (int i = 0; i < t.l2l_count[src]; i++) {
     const int d = t.l2l_conn[src][i];
     if (skip_get(g, src, d)) continue;
@@ -216,6 +241,7 @@ CAAA_HD_NOINLINE void add_valid_land_moves(Game* g, const RunCtx& cx, int src, i
     g->vm[n++] = (uint8_t)d;
   }
   if (!unloadable)
+#pragma unroll 1
     for (int i = 0; i < t.l2s_count[src]; i++) {
       const int ds = t.l2s_conn[src][i];
       if (g->small_cargo[ds] == 0) continue;
@@ -228,12 +254,13 @@ CAAA_HD_NOINLINE void add_valid_land_moves(Game* g, const RunCtx& cx, int src, i
 }
 
 // add_valid_sea_moves / add_valid_sub_moves 1518-1586; `blocked_shift` selects the sea (0) or sub (16) flags
-CAAA_HD void add_valid_sea_moves(Game* g, const RunCtx& cx, int src_sea, int moves, uint32_t blocked_shift) {
-  const CaaaTables& t = cx.T->t;
+CAAA_HD void add_valid_sea_moves(Game* g, const RunCtx cx, int src_sea, int moves, uint32_t blocked_shift) {
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cs = g->canal_state, sa = src_sea + NL;
   uint32_t n = g->nvm;
   const bool two = moves == 2;
   const int cnt = two ? t.seas_within_2_count[cs][src_sea] : t.seas_within_1_count[cs][src_sea];
+#pragma unroll 1
   for (int i = 0; i < cnt; i++) {
     const int d = two ? t.seas_within_2[cs][src_sea][i] : t.seas_within_1[cs][src_sea][i];
     if (two && ((g->seasub_blocked >> (blocked_shift + src_sea * NS + d)) & 1u)) continue;
@@ -244,8 +271,8 @@ CAAA_HD void add_valid_sea_moves(Game* g, const RunCtx& cx, int src_sea, int mov
 }
 
 // ---- conquer_land, 1918-1984 ----
-CAAA_HD_NOINLINE void conquer_land(Game* g, const RunCtx& cx, int dst) {
-  const CaaaTables& t = cx.T->t;
+CAAA_HD_NOINLINE void conquer_land(Game* g, const RunCtx cx, int dst) {
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   const int old = g->owner[dst];
   if (t.capital[old] == dst) {
@@ -261,8 +288,10 @@ CAAA_HD_NOINLINE void conquer_land(Game* g, const RunCtx& cx, int dst) {
   g->nfact[old]--;
   const int n_old = g->nfact[old];
   uint8_t* fl = &g->factloc[0][0];  // flat like the reference's int[6][5]: the shift may read the next row's first entry
+#pragma unroll 1
   for (int i = 0; i < n_old; i++)
     if (g->factloc[old][i] == dst) {
+#pragma unroll 1
       for (int j = i; j < n_old; j++) fl[old * NL + j] = fl[old * NL + j + 1];
       break;
     }
@@ -270,26 +299,33 @@ CAAA_HD_NOINLINE void conquer_land(Game* g, const RunCtx& cx, int dst) {
 
 // ---- phase 0: move_fighter_units, 1657-1803, 3385-3407 ----
 // returns bit masks (bit a = air location a): lo byte canFighterLandHere, next byte canFighterLandIn1Move
-CAAA_HD_NOINLINE uint32_t fighter_landing_masks(Game* g, const RunCtx& cx) {  // pre_move_fighter_units 1657-1714
-  const CaaaTables& t = cx.T->t;
+CAAA_HD_NOINLINE uint32_t fighter_landing_masks(Game* g, const RunCtx cx) {  // pre_move_fighter_units 1657-1714
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   uint32_t here = 0;
+#pragma unroll 1
   for (int l = 0; l < NL; l++) {
     if (owner_allied(g, cx, l) && g->flagged[l] == 0) here |= 1u << l;
     if (owner_rel(g, l) == g->player && g->factory_max[l] > 0)  // 1676: relative owner vs absolute player
+#pragma unroll 1
       for (int i = 0; i < t.l2s_count[l]; i++) here |= 1u << (NL + t.l2s_conn[l][i]);
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
     if (g->carriers[s] <= 0) continue;
     here |= 1u << (s + NL);
     if (su_ptr(g, s, CARRIERS)[2] > 0)  // 1688: carriers[2] aliases cruisers[0]
+#pragma unroll 1
       for (int i = 0; i < t.s2s_count[s]; i++) {
         const int s1 = t.s2s_conn[s][i];
         here |= 1u << (NL + s1);
+#pragma unroll 1
         for (int j = 0; j < t.s2s_count[s1]; j++) here |= 1u << (NL + t.s2s_conn[s1][j]);
       }
   }
   uint32_t in1 = 0;
+#pragma unroll 1
   for (int a = 0; a < NA; a++)
+#pragma unroll 1
     for (int i = 0; i < t.air_conn_count[a]; i++)
       if ((here >> t.air_conn[a][i]) & 1) {
         in1 |= 1u << a;
@@ -299,21 +335,28 @@ CAAA_HD_NOINLINE uint32_t fighter_landing_masks(Game* g, const RunCtx& cx) {  //
 }
 
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_fighter_units(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_fighter_units(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_FIGHTERS)) != 0);
   if (!(g->work & W(CAAA_PH_MOVE_FIGHTERS))) return false;
-  const CaaaTables& t = cx.T->t;
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   uint32_t masks = 0;
   int src = 0;
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
+#pragma unroll 1
     for (; src < NA; src++) {
       arr = air_fighters(g, src);
       if (arr[4] != 0) break;
       fresh = true;
     }
-    if (src >= NA) break;
+    if (src >= NA) {
+      active = false;
+      continue;
+    }
     if (fresh) {
       fresh = false;
       if (!processed) {
@@ -322,6 +365,7 @@ CAAA_HD_NOINLINE bool move_fighter_units(Game* g, const RunCtx& cx) {
       }
       g->vm[0] = (uint8_t)src;
       uint32_t n = 1;
+#pragma unroll 1
       for (int i = 0; i < t.air_within_count[3][src]; i++) {  // add_valid_fighter_moves(src, 4)
         const int d = t.air_within[3][src][i];
         const int dist = t.air_dist[src][d];
@@ -335,7 +379,11 @@ CAAA_HD_NOINLINE bool move_fighter_units(Game* g, const RunCtx& cx) {
     }
     uint32_t dst = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       dst = ai_input<EXPAND>(g, cx);
     }
     update_move_history_4air(g, (uint32_t)src, dst);
@@ -367,56 +415,74 @@ CAAA_HD_NOINLINE bool move_fighter_units(Game* g, const RunCtx& cx) {
     arr[4]--;
     g->work |= W(CAAA_PH_LAND_FIGHTERS);
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_FIGHTERS);
   return false;
 }
 
 // ---- phase 1: move_bomber_units, 1805-1916, 3423-3443 ----
-CAAA_HD uint32_t bomber_here_mask(const Game* g, const RunCtx& cx) {  // 1808-1812, 3557-3563 (lands only)
+CAAA_HD uint32_t bomber_here_mask(const Game* g, const RunCtx cx) {  // 1808-1812, 3557-3563 (lands only)
   uint32_t here = 0;
+#pragma unroll 1
   for (int l = 0; l < NL; l++)
     if (owner_allied(g, cx, l) && g->flagged[l] == 0) here |= 1u << l;
   return here;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m0 = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_BOMBERS)) != 0);
   if (!(g->work & W(CAAA_PH_MOVE_BOMBERS))) return false;
-  const CaaaTables& t = cx.T->t;
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   // the landing masks are phase-local here (the reference keeps them in globals, but re-derives them
   // before every use), so nothing happens without unmoved bombers
   bool any = false;
+#pragma unroll 1
   for (int l = 0; l < NL; l++) any |= lu_ptr(g, l, BOMBERS_LAND_AIR)[6] != 0;
+  const unsigned m = vote_ballot<!EXPAND>(m0, any);
   if (!any) {
     g->work &= ~W(CAAA_PH_MOVE_BOMBERS);
     return false;
   }
   const uint32_t here = bomber_here_mask(g, cx);
   uint32_t in1 = 0, in2 = 0;
+#pragma unroll 1
   for (int l = 0; l < NL; l++)
+#pragma unroll 1
     for (int i = 0; i < t.l2l_count[l]; i++)
       if ((here >> t.l2l_conn[l][i]) & 1) { in1 |= 1u << l; break; }
+#pragma unroll 1
   for (int s = 0; s < NS; s++)
+#pragma unroll 1
     for (int i = 0; i < t.s2l_count[s]; i++)
       if ((here >> t.s2l_conn[s][i]) & 1) { in1 |= 1u << (NL + s); break; }
+#pragma unroll 1
   for (int a = 0; a < NA; a++)
+#pragma unroll 1
     for (int i = 0; i < t.air_conn_count[a]; i++)
       if ((in1 >> t.air_conn[a][i]) & 1) { in2 |= 1u << a; break; }
   bool fresh = true;
   int src = 0;
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
+#pragma unroll 1
     for (; src < NL; src++) {
       arr = lu_ptr(g, src, BOMBERS_LAND_AIR);
       if (arr[6] != 0) break;
       fresh = true;
     }
-    if (src >= NL) break;
+    if (src >= NL) {
+      active = false;
+      continue;
+    }
     if (fresh) {
       fresh = false;
       g->vm[0] = (uint8_t)src;
       uint32_t n = 1;
+#pragma unroll 1
       for (int i = 0; i < t.air_within_count[5][src]; i++) {  // add_valid_bomber_moves(src, 6)
         const int d = t.air_within[5][src][i];
         const int dist = t.air_dist[src][d];
@@ -432,7 +498,11 @@ CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx& cx) {
     }
     uint32_t dst = g->vm[0];
     if (g->nvm == 1) {  // 1860: inverted test
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       dst = ai_input<EXPAND>(g, cx);
     }
     if ((uint32_t)src == dst) {
@@ -457,6 +527,7 @@ CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx& cx) {
     arr[6]--;
     g->work |= W(CAAA_PH_LAND_BOMBERS);
   }
+  if (stop) return true;
   clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_BOMBERS);
   return false;
@@ -464,14 +535,18 @@ CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx& cx) {
 
 // ---- phase 2: stage_transport_units, 1588-1655 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_STAGE_TRANSPORTS)) != 0);
   if (!(g->work & W(CAAA_PH_STAGE_TRANSPORTS))) return false;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int cell = 0;  // (ut - TRANS_EMPTY) * NS + sea, in the reference's loop order
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0, staging = 0;
+#pragma unroll 1
     for (; cell < 4 * NS; cell++) {
       ut = TRANS_EMPTY + cell / NS;
       s = cell % NS;
@@ -480,7 +555,10 @@ CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx& cx) {
       if (arr[staging] != 0) break;
       fresh = true;
     }
-    if (cell >= 4 * NS) break;
+    if (cell >= 4 * NS) {
+      active = false;
+      continue;
+    }
     const int done = staging - 1;
     const uint32_t sa = (uint32_t)(s + NL);
     if (fresh) {
@@ -492,7 +570,11 @@ CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx& cx) {
     processed = true;
     uint32_t da = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       da = ai_input<EXPAND>(g, cx);
     }
     g->work |= W(CAAA_PH_MOVE_TRANSPORTS) | W(CAAA_PH_UNLOAD_TRANSPORTS);
@@ -503,7 +585,7 @@ CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx& cx) {
     }
     const int ds = (int)da - NL;
     const unsigned flat = (unsigned)(s * NS) + da;  // 1630: sea_dist indexed with an air id (P1 iii)
-    const int dist = flat < 9u ? ((const uint8_t*)cx.T->t.sea_dist[g->canal_state])[flat] : 0;
+    const int dist = flat < 9u ? ((const uint8_t*)CAAA_TAB(cx)->t.sea_dist[g->canal_state])[flat] : 0;
     if (g->blockade[ds] > 0) {
       flag_combat(g, da, 2);
       continue;  // not moved: the choice is drawn again
@@ -521,6 +603,7 @@ CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx& cx) {
       g->large_cargo[ds]++;
     }
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_STAGE_TRANSPORTS);
   return false;
@@ -528,16 +611,20 @@ CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx& cx) {
 
 // ---- phases 3,4,5,12: move_land_unit_type, 1986-2060 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx& cx, int ut, int ph) {
+CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx cx, unsigned min, int ut, int ph) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(ph)) != 0);
   if (!(g->work & W(ph))) return false;
-  const CaaaTables& t = cx.T->t;
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   const int mm = max_move_land(ut);
   bool processed = false, fresh = true;
   int cell = 0;  // src * mm + (mm - moves)
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
     int src = 0, moves = 0;
+#pragma unroll 1
     for (; cell < NL * mm; cell++) {
       src = cell / mm;
       moves = mm - cell % mm;
@@ -545,7 +632,10 @@ CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx& cx, int ut, int
       if (arr[moves] != 0) break;
       fresh = true;
     }
-    if (cell >= NL * mm) break;
+    if (cell >= NL * mm) {
+      active = false;
+      continue;
+    }
     if (fresh) {
       fresh = false;
       processed = true;
@@ -555,7 +645,11 @@ CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx& cx, int ut, int
     }
     uint32_t dst = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       dst = ai_input<EXPAND>(g, cx);
     }
     if ((uint32_t)src == dst) {
@@ -591,6 +685,7 @@ CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx& cx, int ut, int
       flag_combat(g, dst, 2);
     }
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(ph);
   return false;
@@ -598,9 +693,11 @@ CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx& cx, int ut, int
 
 // ---- phase 6: move_transport_units, 2062-2159 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_TRANSPORTS)) != 0);
   if (!(g->work & W(CAAA_PH_MOVE_TRANSPORTS))) return false;
   const int cur = g->cur;
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {  // skip_empty_transports 2062-2075
     uint8_t* e = su_ptr(g, s, TRANS_EMPTY);
     const uint32_t n = e[1] + e[2] + e[3];
@@ -611,9 +708,12 @@ CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx& cx) {
   }
   bool processed = false, fresh = true;
   int cell = 0;  // ((ut - TRANS_1I) * NS + sea) * 2 + (i - 1); every loaded type has max_state 4
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0, cs = 0;
+#pragma unroll 1
     for (; cell < 6 * NS * 2; cell++) {
       ut = TRANS_1I + cell / (NS * 2);
       s = (cell / 2) % NS;
@@ -622,7 +722,10 @@ CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx& cx) {
       if (arr[cs] != 0) break;
       fresh = true;
     }
-    if (cell >= 6 * NS * 2) break;
+    if (cell >= 6 * NS * 2) {
+      active = false;
+      continue;
+    }
     const uint32_t sa = (uint32_t)(s + NL);
     if (fresh) {
       fresh = false;
@@ -633,7 +736,11 @@ CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx& cx) {
     }
     uint32_t da = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       da = ai_input<EXPAND>(g, cx);
     }
     const int ds = (int)da - NL;
@@ -659,6 +766,7 @@ CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx& cx) {
       }
     }
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_TRANSPORTS);
   return false;
@@ -666,19 +774,26 @@ CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx& cx) {
 
 // ---- phase 7: move_subs, 2160-2214 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_subs(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_subs(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_SUBS)) != 0);
   if (!(g->work & W(CAAA_PH_MOVE_SUBS))) return false;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int s = 0;
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
+#pragma unroll 1
     for (; s < NS; s++) {
       arr = su_ptr(g, s, SUBMARINES);
       if (arr[2] != 0) break;
       fresh = true;
     }
-    if (s >= NS) break;
+    if (s >= NS) {
+      active = false;
+      continue;
+    }
     const uint32_t sa = (uint32_t)(s + NL);
     if (fresh) {
       fresh = false;
@@ -689,7 +804,11 @@ CAAA_HD_NOINLINE bool move_subs(Game* g, const RunCtx& cx) {
     processed = true;
     uint32_t da = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       da = ai_input<EXPAND>(g, cx);
     }
     const int ds = (int)da - NL;
@@ -706,17 +825,20 @@ CAAA_HD_NOINLINE bool move_subs(Game* g, const RunCtx& cx) {
     uts(g, cur, s)[SUBMARINES]--;
     g->tot_sea[cur][s]--;
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_SUBS);
   return false;
 }
 
 // ---- phase 8: move_destroyers_battleships, 2216-2310 ----
-CAAA_HD void carry_allied_fighters(Game* g, const RunCtx& cx, int src, int dst) {  // 2286-2310
+CAAA_HD void carry_allied_fighters(Game* g, const RunCtx cx, int src, int dst) {  // 2286-2310
   int moved = 0;
+#pragma unroll 1
   for (int p = 1; p < NP; p++) {
     const int pa = (g->cur + p) % NP;
     if (!allied(g, cx, pa)) continue;
+#pragma unroll 1
     while (uts(g, pa, src)[FIGHTERS] > 0) {
       uts(g, pa, src)[FIGHTERS]--;
       g->tot_sea[pa][src]--;
@@ -728,14 +850,18 @@ CAAA_HD void carry_allied_fighters(Game* g, const RunCtx& cx, int src, int dst) 
   }
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_destroyers_battleships(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool move_destroyers_battleships(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_SHIPS)) != 0);
   if (!(g->work & W(CAAA_PH_MOVE_SHIPS))) return false;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int cell = 0;  // (ut - DESTROYERS) * NS + sea
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0, unmoved = 0;
+#pragma unroll 1
     for (; cell < 5 * NS; cell++) {
       ut = DESTROYERS + cell / NS;
       s = cell % NS;
@@ -744,7 +870,10 @@ CAAA_HD_NOINLINE bool move_destroyers_battleships(Game* g, const RunCtx& cx) {
       if (arr[unmoved] != 0) break;
       fresh = true;
     }
-    if (cell >= 5 * NS) break;
+    if (cell >= 5 * NS) {
+      active = false;
+      continue;
+    }
     const int done = done_moving_sea(ut);
     const uint32_t sa = (uint32_t)(s + NL);
     if (fresh) {
@@ -756,7 +885,11 @@ CAAA_HD_NOINLINE bool move_destroyers_battleships(Game* g, const RunCtx& cx) {
     }
     uint32_t da = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       da = ai_input<EXPAND>(g, cx);
     }
     if (g->enemy_count[da] > 0) flag_combat(g, da, 2);
@@ -774,6 +907,7 @@ CAAA_HD_NOINLINE bool move_destroyers_battleships(Game* g, const RunCtx& cx) {
     g->tot_sea[cur][s]--;
     if (ut == CARRIERS) carry_allied_fighters(g, cx, s, ds);
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_SHIPS);
   return false;
@@ -794,11 +928,13 @@ CAAA_HD bool take_hits(uint8_t* n, uint32_t& hits, uint32_t& taken) {
   taken = hits;
   return true;
 }
-CAAA_HD_NOINLINE void remove_land_defenders(Game* g, const RunCtx& cx, int land, uint32_t hits) {  // 2613-2641
-  const int ne = cx.T->n_enemies[g->cur];
-  const uint8_t* en = cx.T->enemies_abs[g->cur];
+CAAA_HD_NOINLINE void remove_land_defenders(Game* g, const RunCtx cx, int land, uint32_t hits) {  // 2613-2641
+  const int ne = CAAA_TAB(cx)->n_enemies[g->cur];
+  const uint8_t* en = CAAA_TAB(cx)->enemies_abs[g->cur];
+#pragma unroll 1
   for (int k = 0; k < 6; k++) {
     const int ut = order_land_def(k);
+#pragma unroll 1
     for (int e = 0; e < ne; e++) {
       const int pa = en[e];
       uint8_t* n = &utl(g, pa, land)[ut];
@@ -814,6 +950,7 @@ CAAA_HD_NOINLINE void remove_land_defenders(Game* g, const RunCtx& cx, int land,
 CAAA_HD_NOINLINE void remove_land_attackers(Game* g, int land, uint32_t hits) {  // 2642-2698
   const int cur = g->cur;
   uint8_t* mine = utl(g, cur, land);
+#pragma unroll 1
   for (int ut = INFANTRY; ut <= TANKS; ut++) {  // ORDER_OF_LAND_ATTACKERS_1, state 0 only
     uint8_t* n = &lu_ptr(g, land, ut)[0];
     if (*n == 0) continue;
@@ -826,8 +963,10 @@ CAAA_HD_NOINLINE void remove_land_attackers(Game* g, int land, uint32_t hits) { 
     }
     mine[ut] = 0;
   }
+#pragma unroll 1
   for (int ut = FIGHTERS; ut <= BOMBERS_LAND_AIR; ut++) {  // ORDER_OF_LAND_ATTACKERS_2, states 1..n-2
     if (mine[ut] == 0) continue;
+#pragma unroll 1
     for (int s = 1; s < (int)states_land(ut) - 1; s++) {
       uint8_t* n = &lu_ptr(g, land, ut)[s];
       if (*n == 0) continue;
@@ -839,9 +978,10 @@ CAAA_HD_NOINLINE void remove_land_attackers(Game* g, int land, uint32_t hits) { 
     }
   }
 }
-CAAA_HD_NOINLINE void remove_sea_defenders(Game* g, const RunCtx& cx, int sea, uint32_t hits, bool submerged) {  // 2700-2806
-  const int ne = cx.T->n_enemies[g->cur], air = sea + NL;
-  const uint8_t* en = cx.T->enemies_abs[g->cur];
+CAAA_HD_NOINLINE void remove_sea_defenders(Game* g, const RunCtx cx, int sea, uint32_t hits, bool submerged) {  // 2700-2806
+  const int ne = CAAA_TAB(cx)->n_enemies[g->cur], air = sea + NL;
+  const uint8_t* en = CAAA_TAB(cx)->enemies_abs[g->cur];
+#pragma unroll 1
   for (int e = 0; e < ne; e++) {  // battleships absorb one hit each
     uint8_t* su = uts(g, en[e], sea);
     if (su[BATTLESHIPS] == 0) continue;
@@ -850,9 +990,11 @@ CAAA_HD_NOINLINE void remove_sea_defenders(Game* g, const RunCtx& cx, int sea, u
     su[BS_DAMAGED] = (uint8_t)(su[BS_DAMAGED] + taken);
     if (done) return;
   }
+#pragma unroll 1
   for (int k = submerged ? 1 : 0; k < 13; k++) {
     const int ut = order_sea_def(k);
     const bool in_blockade_range = k >= DESTROYERS && k <= BS_DAMAGED;  // 2783,2791: order index vs type ids
+#pragma unroll 1
     for (int e = 0; e < ne; e++) {
       const int pa = en[e];
       uint8_t* n = &uts(g, pa, sea)[ut];
@@ -908,10 +1050,12 @@ CAAA_HD_NOINLINE void remove_sea_attackers(Game* g, int sea, uint32_t hits) {  /
   if (hit_sea_state0(g, sea, DESTROYERS, hits)) return;
   if (hit_sea_state0(g, sea, CARRIERS, hits)) return;
   if (hit_sea_state0(g, sea, CRUISERS, hits)) return;
+#pragma unroll 1
   for (int k = 0; k < 2; k++) {  // air units in any state, 2915-2942
     const int ut = k == 0 ? (int)FIGHTERS : (int)BOMBERS_SEA;
     uint8_t* c = cur_sea(g, sea, ut);
     if (*c == 0) continue;
+#pragma unroll 1
     for (int s = 0; s < 5; s++) {
       uint8_t* n = &su_ptr(g, sea, ut)[s];
       if (*n == 0) continue;
@@ -922,6 +1066,7 @@ CAAA_HD_NOINLINE void remove_sea_attackers(Game* g, int sea, uint32_t hits) {  /
       if (done) return;
     }
   }
+#pragma unroll 1
   for (int k = 0; k < 8; k++)
     if (hit_sea_state0(g, sea, order_sea_att3(k), hits)) return;
 }
@@ -929,6 +1074,7 @@ CAAA_HD_NOINLINE void remove_sea_attackers(Game* g, int sea, uint32_t hits) {  /
 // ---- phase 9: resolve_sea_battles, 2312-2550, 2582-2603 ----
 CAAA_HD void sea_retreat(Game* g, int src, int dst) {  // 2582-2603
   const int cur = g->cur;
+#pragma unroll 1
   for (int ut = TRANS_EMPTY; ut <= BS_DAMAGED; ut++) {
     const uint32_t n = uts(g, cur, src)[ut];
     uint8_t* d = su_ptr(g, dst, ut);
@@ -943,28 +1089,37 @@ CAAA_HD void sea_retreat(Game* g, int src, int dst) {  // 2582-2603
   g->flagged[src + NL] = 0;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W_SEA_BATTLE) != 0);
   if (!(g->work & W_SEA_BATTLE)) return false;
-  const CaaaTables& t = cx.T->t;
-  const int cur = g->cur, ne = cx.T->n_enemies[cur];
-  const uint8_t* en = cx.T->enemies_abs[cur];
+  const CaaaTables& t = CAAA_TAB(cx)->t;
+  const int cur = g->cur, ne = CAAA_TAB(cx)->n_enemies[cur];
+  const uint8_t* en = CAAA_TAB(cx)->enemies_abs[cur];
   int s = 0, rounds = 0;
   bool in_battle = false, submerged = false;
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     if (!in_battle) {  // next flagged sea with own units (one sea per iteration keeps the lanes together)
+#pragma unroll 1
       for (; s < NS; s++)
         if (g->flagged[s + NL] != 0 && g->tot_sea[cur][s] != 0) break;
-      if (s >= NS) break;
+      if (s >= NS) {
+        active = false;
+        continue;
+      }
       const uint8_t* mine0 = uts(g, cur, s);
       submerged = mine0[DESTROYERS] == 0;
       bool skip = false;
       if (g->tot_sea[cur][s] == 2) {  // 2336: literal "== 2"
         if (submerged) {
           uint32_t subs = 0;
+#pragma unroll 1
           for (int e = 0; e < ne; e++) subs += uts(g, en[e], s)[SUBMARINES];
           if ((int)(subs & 0xffu) == g->enemy_count[s]) skip = true;  // 2344: land index
         }
         if (!skip)
+#pragma unroll 1
           for (int ut = CRUISERS; ut <= BS_DAMAGED; ut++) {  // bombardment no longer possible
             uint8_t* a = su_ptr(g, s, ut);
             a[0] = (uint8_t)(a[0] + a[1]);
@@ -984,7 +1139,9 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
     bool over = false;
     if (rounds >= SEA_ROUND_CAP) {  // guard (not in the reference, which would spin for ever)
       g->status |= CAAA_ERR_SEA_ROUND_CAP;
-      return true;
+      stop = true;
+      active = false;
+      continue;
     }
     rounds++;
     if (g->flagged[air] == 1) {  // retreat option, 2368-2406
@@ -993,6 +1150,7 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
                   mine[BATTLESHIPS] + mine[BS_DAMAGED] > 0 ||
           g->blockade[s] == 0)
         g->vm[n++] = (uint8_t)air;
+#pragma unroll 1
       for (int i = 0; i < t.s2s_count[s]; i++) {
         const int d = t.s2s_conn[s][i];
         if (g->blockade[d] == 0) g->vm[n++] = (uint8_t)(d + NL);
@@ -1001,7 +1159,11 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
       if (n > 0) {
         uint32_t da = g->vm[0];
         if (n > 1) {
-          if (g->answers_remaining == 0) return true;
+          if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
           da = ai_input<EXPAND>(g, cx);
         }
         const int ds = (uint8_t)(da - NL);
@@ -1018,14 +1180,17 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
         targets = g->enemy_count[air] > 0;
       } else if (mine[CARRIERS] + mine[CRUISERS] + mine[BATTLESHIPS] + mine[BS_DAMAGED] > 0) {
         if (g->enemy_count[air] > 0)
+#pragma unroll 1
           for (int e = 0; e < ne; e++)
             if (g->tot_sea[en[e]][s] - uts(g, en[e], s)[SUBMARINES] > 0) { targets = true; break; }
       } else if (mine[SUBMARINES] > 0) {
+#pragma unroll 1
         for (int e = 0; e < ne; e++) {
           const uint8_t* eu = uts(g, en[e], s);
           if (g->tot_sea[en[e]][s] - (eu[FIGHTERS] + eu[SUBMARINES]) > 0) { targets = true; break; }
         }
       } else if (mine[FIGHTERS] + g->cur_sea_bombers[s] > 0) {
+#pragma unroll 1
         for (int e = 0; e < ne; e++)
           if (g->tot_sea[en[e]][s] - uts(g, en[e], s)[SUBMARINES] > 0) { targets = true; break; }
       }
@@ -1034,6 +1199,7 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
           g->tot_sea[cur][s] = (int16_t)(g->tot_sea[cur][s] - mine[TRANS_EMPTY]);
           mine[TRANS_EMPTY] = 0;
           su_ptr(g, s, TRANS_EMPTY)[0] = 0;
+#pragma unroll 1
           for (int ut = TRANS_1I; ut <= TRANS_1I_1T; ut++) {
             g->tot_sea[cur][s] = (int16_t)(g->tot_sea[cur][s] - mine[ut]);
             mine[ut] = 0;
@@ -1050,6 +1216,7 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
       uint32_t ahits = attacker_hits(g, cx, admg);
       if (!submerged) {
         int ddmg = 0;
+#pragma unroll 1
         for (int e = 0; e < ne; e++) ddmg += uts(g, en[e], s)[SUBMARINES];
         const uint32_t dhits = defender_hits(g, cx, ddmg);
         if (dhits > 0) remove_sea_attackers(g, s, dhits);
@@ -1060,6 +1227,7 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
              mine[FIGHTERS] * 3 + g->cur_sea_bombers[s] * 4;
       ahits = attacker_hits(g, cx, admg);
       int ddmg = 0;
+#pragma unroll 1
       for (int e = 0; e < ne; e++)  // 2527-2530: type ids 0..4 (only fighters have a defence value) + fighters again
         ddmg += uts(g, en[e], s)[FIGHTERS] * 4 * 2;
       const uint32_t dhits = defender_hits(g, cx, ddmg);
@@ -1075,21 +1243,26 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx& cx) {
       s++;
     }
   }
+  if (stop) return true;
   g->work &= ~W_SEA_BATTLE;
   return false;
 }
 
 // ---- phase 10: unload_transports, 2984-3053, 3373-3383 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_UNLOAD_TRANSPORTS)) != 0);
   if (!(g->work & W(CAAA_PH_UNLOAD_TRANSPORTS))) return false;
-  const CaaaTables& t = cx.T->t;
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int cell = 0;  // (ut - TRANS_1I) * NS + sea
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0;
+#pragma unroll 1
     for (; cell < 6 * NS; cell++) {
       ut = TRANS_1I + cell / NS;
       s = cell % NS;
@@ -1097,13 +1270,17 @@ CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx& cx) {
       if (arr[1] != 0) break;  // STATES_UNLOADING is 1 for every loaded transport type
       fresh = true;
     }
-    if (cell >= 6 * NS) break;
+    if (cell >= 6 * NS) {
+      active = false;
+      continue;
+    }
     const uint32_t sa = (uint32_t)(s + NL);
     if (fresh) {
       fresh = false;
       processed = true;
       g->vm[0] = (uint8_t)sa;
       uint32_t n = 1;
+#pragma unroll 1
       for (int i = 0; i < t.s2l_count[s]; i++) {
         const int d = t.s2l_conn[s][i];
         if (!skip_get(g, sa, d)) g->vm[n++] = (uint8_t)d;
@@ -1112,7 +1289,11 @@ CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx& cx) {
     }
     uint32_t dst = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       dst = ai_input<EXPAND>(g, cx);
     }
     if (sa == dst) {
@@ -1141,6 +1322,7 @@ CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx& cx) {
       if (g->enemy_count[dst] == 0) conquer_land(g, cx, dst);
     }
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_UNLOAD_TRANSPORTS);
   return false;
@@ -1150,6 +1332,7 @@ CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx& cx) {
 CAAA_HD void hit_air_states(Game* g, int land, int ut, int lo, int hi, uint32_t& hits, bool stop_on_absorb) {
   // shared shape of the strategic-bombing / AA-fire casualty loops (3103-3117, 3179-3210)
   const int cur = g->cur;
+#pragma unroll 1
   for (int s = lo; s < hi; s++) {
     uint32_t taken;
     const bool done = take_hits(&lu_ptr(g, land, ut)[s], hits, taken);
@@ -1162,19 +1345,26 @@ CAAA_HD void hit_air_states(Game* g, int land, int ut, int lo, int hi, uint32_t&
   }
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W_LAND_BATTLE) != 0);
   if (!(g->work & W_LAND_BATTLE)) return false;
-  const CaaaTables& t = cx.T->t;
-  const int cur = g->cur, ne = cx.T->n_enemies[cur];
-  const uint8_t* en = cx.T->enemies_abs[cur];
+  const CaaaTables& t = CAAA_TAB(cx)->t;
+  const int cur = g->cur, ne = CAAA_TAB(cx)->n_enemies[cur];
+  const uint8_t* en = CAAA_TAB(cx)->enemies_abs[cur];
   int l = 0;
   uint32_t rounds = 0;
   bool in_battle = false;
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     if (!in_battle) {
+#pragma unroll 1
       for (; l < NL; l++)
         if (g->flagged[l] != 0 && g->tot_land[cur][l] != 0) break;
-      if (l >= NL) break;
+      if (l >= NL) {
+        active = false;
+        continue;
+      }
       uint8_t* mine = utl(g, cur, l);
       int16_t* my_total = &g->tot_land[cur][l];
       bool skip = false;
@@ -1192,9 +1382,12 @@ CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx& cx) {
         } else {
           if (g->bombard_max[l] > 0) {  // shore bombardment 3134-3158
             int admg = 0;
+#pragma unroll 1
             for (int ut = BS_DAMAGED; ut >= CRUISERS; ut--)
+#pragma unroll 1
               for (int i = 0; i < t.l2s_count[l]; i++) {
                 uint8_t* ships = su_ptr(g, t.l2s_conn[l][i], ut);
+#pragma unroll 1
                 while (ships[1] > 0 && g->bombard_max[l] > 0) {
                   admg += attack_sea(ut);
                   ships[0]++;
@@ -1209,6 +1402,7 @@ CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx& cx) {
           const uint32_t air_units = (uint8_t)(mine[FIGHTERS] + mine[BOMBERS_LAND_AIR]);  // AA fire 3160-3216
           if (air_units > 0) {
             int aa = 0;
+#pragma unroll 1
             for (int e = 0; e < ne; e++) aa += utl(g, en[e], l)[AA_GUNS];
             if (aa > 0) {
               uint32_t dh = defender_hits(g, cx, (uint8_t)(air_units * 3));
@@ -1240,6 +1434,7 @@ CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx& cx) {
     if (!over && g->flagged[l] == 1) {  // retreat option 3256-3299
       g->vm[0] = (uint8_t)l;
       uint32_t n = 1;
+#pragma unroll 1
       for (int i = 0; i < t.l2l_count[l]; i++) {
         const int d = t.l2l_conn[l][i];
         if (g->enemy_count[d] == 0 && g->flagged[d] == 0 && owner_allied(g, cx, d)) g->vm[n++] = (uint8_t)d;
@@ -1247,11 +1442,16 @@ CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx& cx) {
       g->nvm = (uint8_t)n;
       uint32_t dst = g->vm[0];
       if (n > 1) {
-        if (g->answers_remaining == 0) return true;
+        if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
         dst = ai_input<EXPAND>(g, cx);
       }
       if ((uint32_t)l != dst || rounds > 100) {
         const int dl = dst < (uint32_t)NL ? (int)dst : l;  // dst is always a land here
+#pragma unroll 1
         for (int ut = INFANTRY; ut <= TANKS; ut++) {
           const uint32_t k = lu_ptr(g, l, ut)[0];
           lu_ptr(g, dl, ut)[0] = (uint8_t)(lu_ptr(g, dl, ut)[0] + k);
@@ -1272,6 +1472,7 @@ CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx& cx) {
       const uint32_t ahits = attacker_hits(g, cx, admg);
       int ddmg = 0;
       uint32_t dh = 0;
+#pragma unroll 1
       for (int e = 0; e < ne; e++) {  // 3319-3327: one draw per enemy player, the last one counts
         const uint8_t* eu = utl(g, en[e], l);
         ddmg += eu[INFANTRY] * 2 + eu[ARTILLERY] * 2 + eu[TANKS] * 3 + eu[FIGHTERS] * 4 + eu[BOMBERS_LAND_AIR];
@@ -1291,34 +1492,42 @@ CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx& cx) {
       l++;
     }
   }
+  if (stop) return true;
   g->work &= ~W_LAND_BATTLE;
   return false;
 }
 
 // ---- phases 13/14: land_fighter_units / land_bomber_units, 3409-3421, 3445-3654 ----
-CAAA_HD uint32_t fighter_final_landing_mask(Game* g, const RunCtx& cx) {  // refresh_can_fighter_land_here 3445-3466
-  const CaaaTables& t = cx.T->t;
+CAAA_HD uint32_t fighter_final_landing_mask(Game* g, const RunCtx cx) {  // refresh_can_fighter_land_here 3445-3466
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   uint32_t here = 0;
+#pragma unroll 1
   for (int s = 0; s < NS; s++)
     if (g->carriers[s] > 0) here |= 1u << (s + NL);
+#pragma unroll 1
   for (int l = 0; l < NL; l++) {
     if (owner_allied(g, cx, l) && g->flagged[l] == 0) here |= 1u << l;
     if (g->factory_max[l] > 0 && owner_rel(g, l) == g->player)
+#pragma unroll 1
       for (int i = 0; i < t.l2s_count[l]; i++) here |= 1u << (NL + t.l2s_conn[l][i]);
   }
   return here;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_LAND_FIGHTERS)) != 0);
   if (!(g->work & W(CAAA_PH_LAND_FIGHTERS))) return false;
-  const CaaaTables& t = cx.T->t;
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   uint32_t here = 0;
   int cell = 0;  // (state - 1) * NA + src
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
     int src = 0, cs = 0;
+#pragma unroll 1
     for (; cell < 3 * NA; cell++) {
       cs = 1 + cell / NA;
       src = cell % NA;
@@ -1326,7 +1535,10 @@ CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx& cx) {
       if (arr[cs] != 0) break;
       fresh = true;
     }
-    if (cell >= 3 * NA) break;
+    if (cell >= 3 * NA) {
+      active = false;
+      continue;
+    }
     if (fresh) {
       fresh = false;
       if (!processed) {
@@ -1334,6 +1546,7 @@ CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx& cx) {
         here = fighter_final_landing_mask(g, cx);
       }
       uint32_t n = 0;
+#pragma unroll 1
       for (int i = 0; i < t.air_within_count[cs - 1][src]; i++) {  // add_valid_fighter_landing
         const int d = t.air_within[cs - 1][src][i];
         if (((here >> d) & 1) && !skip_get(g, src, d)) g->vm[n++] = (uint8_t)d;
@@ -1343,7 +1556,11 @@ CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx& cx) {
     }
     uint32_t dst = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       dst = ai_input<EXPAND>(g, cx);
     }
     if ((uint32_t)src == dst) {
@@ -1368,21 +1585,26 @@ CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx& cx) {
     }
     arr[cs]--;
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_LAND_FIGHTERS);
   return false;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_LAND_BOMBERS)) != 0);
   if (!(g->work & W(CAAA_PH_LAND_BOMBERS))) return false;
-  const CaaaTables& t = cx.T->t;
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   uint32_t here = 0;
   int cell = 0;  // cur1 * NA + src
-  for (;;) {
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
     uint8_t* arr = nullptr;
     int src = 0, cs = 0;
+#pragma unroll 1
     for (; cell < 5 * NA; cell++) {
       src = cell % NA;
       cs = src < NL ? cell / NA + 1 : cell / NA;
@@ -1390,7 +1612,10 @@ CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx& cx) {
       if (arr[cs] != 0) break;
       fresh = true;
     }
-    if (cell >= 5 * NA) break;
+    if (cell >= 5 * NA) {
+      active = false;
+      continue;
+    }
     if (fresh) {
       fresh = false;
       if (!processed) {
@@ -1399,6 +1624,7 @@ CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx& cx) {
       }
       const int moves = cs + (src < NL ? 0 : 1);
       uint32_t n = 0;
+#pragma unroll 1
       for (int i = 0; i < t.air_to_land_within_count[moves - 1][src]; i++) {  // add_valid_bomber_landing
         const int d = t.air_to_land_within[moves - 1][src][i];
         if ((here >> d) & 1) g->vm[n++] = (uint8_t)d;
@@ -1408,7 +1634,11 @@ CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx& cx) {
     if (g->nvm == 0) g->vm[g->nvm++] = (uint8_t)src;
     uint32_t dst = g->vm[0];
     if (g->nvm > 1) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       dst = ai_input<EXPAND>(g, cx);
     }
     if ((uint32_t)src == dst) {
@@ -1429,6 +1659,7 @@ CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx& cx) {
     }
     arr[cs]--;
   }
+  if (stop) return true;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_LAND_BOMBERS);
   return false;
@@ -1438,14 +1669,20 @@ CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx& cx) {
 // One flat loop: a cell is (factory, adjacent sea) or (factory, the land itself); every iteration is one
 // purchase decision of the cell the lane is at.
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
-  const CaaaTables& t = cx.T->t;
+CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx cx, unsigned min) {
+  const unsigned m = min;
+  const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   int f = 0, si = 0;
   bool new_factory = true, new_cell = true, processed = false;
   uint32_t repair = 0, last = 0;
-  for (;;) {
-    if (f >= g->nfact[cur]) break;
+  bool active = true, stop = false;
+  while (vote_any<!EXPAND>(m, active)) {
+    if (!active) continue;
+    if (f >= g->nfact[cur]) {
+      active = false;
+      continue;
+    }
     const int land = g->factloc[cur][f];
     if (new_factory) {
       if (g->builds_left[land] == 0) {
@@ -1477,6 +1714,7 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
       if (g->factory_hp[land] <= (int)built) repair = (uint8_t)(1 + built - g->factory_hp[land]);
       uint32_t n = 1;
       if (at_sea) {
+#pragma unroll 1
         for (int k = 6; k >= 0; k--) {
           const uint32_t ut = buy_sea(k);
           if (skip_get(g, 0, ut)) {
@@ -1486,12 +1724,14 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
           if (g->money[cur] < cost_sea(ut) + repair) continue;
           if (ut == FIGHTERS) {
             int fighters = 0;
+#pragma unroll 1
             for (int pa = 0; pa < NP; pa++) fighters += uts(g, pa, sea)[FIGHTERS];
             if (g->carriers[sea] * 2 <= fighters) continue;
           }
           g->vm[n++] = (uint8_t)ut;
         }
       } else {
+#pragma unroll 1
         for (int ut = NLT - 1; ut >= 0; ut--) {
           if (skip_get(g, 0, (unsigned)ut)) {
             last = (uint32_t)ut;
@@ -1508,7 +1748,11 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
       }
     }
     if (!close) {
-      if (g->answers_remaining == 0) return true;
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
       processed = true;
       const uint32_t buy = ai_input<EXPAND>(g, cx);
       if (buy == pass) {
@@ -1516,6 +1760,7 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
         close = true;
       } else {
         if (at_sea) {
+#pragma unroll 1
           for (int s2 = si; s2 < t.l2s_count[land]; s2++) g->builds_left[t.l2s_conn[land][s2] + NL]--;
           g->builds_left[land]--;
           g->factory_hp[land] = (int8_t)(g->factory_hp[land] + (int)repair);
@@ -1525,6 +1770,7 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
           g->tot_sea[cur][sea]++;
           (*cur_sea(g, sea, b))++;
           if (buy > last) {
+#pragma unroll 1
             for (uint32_t u = last; u < buy; u++) skip_set(g, 0, u);
             last = buy;
           }
@@ -1537,6 +1783,7 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
           g->tot_land[cur][land]++;
           utl(g, cur, land)[b]++;
           if (buy > last)
+#pragma unroll 1
             for (uint32_t u = last; u < buy; u++) skip_set(g, 0, u);
           last = buy;
         }
@@ -1553,16 +1800,18 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx& cx) {
       }
     }
   }
-  return false;
+  return stop;
 }
 
 // ---- phases 16-19: crash_air_units, reset_units_fully, collect_money, 3836-3894 ----
-CAAA_HD void crash_air_units(Game* g, const RunCtx& cx) {
+CAAA_HD void crash_air_units(Game* g, const RunCtx cx) {
   const int cur = g->cur;
   uint32_t lands_with_fighters = 0;
+#pragma unroll 1
   for (int l = 0; l < NL; l++) lands_with_fighters |= utl(g, cur, l)[FIGHTERS];
   if (lands_with_fighters) {  // the landing mask has no side effects: only derive it when a land holds fighters
     const uint32_t here = fighter_landing_masks(g, cx);
+#pragma unroll 1
     for (int l = 0; l < NL; l++) {
       if ((here >> l) & 1) continue;
       const uint32_t n = utl(g, cur, l)[FIGHTERS];
@@ -1572,10 +1821,12 @@ CAAA_HD void crash_air_units(Game* g, const RunCtx& cx) {
       lu_ptr(g, l, FIGHTERS)[0] = 0;
     }
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
     uint8_t* n = &su_ptr(g, s, FIGHTERS)[0];
     if (*n == 0) continue;  // space is a uint8 >= 0: nothing to lose
     uint32_t space = (uint32_t)(g->carriers[s] * 2);
+#pragma unroll 1
     for (int p = 1; p < NP; p++) space -= uts(g, (cur + p) % NP, s)[FIGHTERS];
     space &= 0xffu;  // uint8 in the reference
     if (space < *n) {
@@ -1588,6 +1839,7 @@ CAAA_HD void crash_air_units(Game* g, const RunCtx& cx) {
 }
 CAAA_HD void reset_units_fully(Game* g) {
   const int cur = g->cur;
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
     uint8_t* mine = uts(g, cur, s);
     const uint32_t dmg = mine[BS_DAMAGED];
@@ -1599,15 +1851,15 @@ CAAA_HD void reset_units_fully(Game* g) {
     mine[BS_DAMAGED] = 0;
   }
 }
-CAAA_HD void collect_money(Game* g, const RunCtx& cx) {
+CAAA_HD void collect_money(Game* g, const RunCtx cx) {
   const int cur = g->cur;
-  if (g->owner[cx.T->t.capital[cur]] == cur) g->money[cur] = (uint8_t)(g->money[cur] + g->income[cur]);
+  if (g->owner[CAAA_TAB(cx)->t.capital[cur]] == cur) g->money[cur] = (uint8_t)(g->money[cur] + g->income[cur]);
 }
 
 // ---- phase 20: rotate_turns, 3895-4029 ----
 // Per-player data is stored in absolute order, so the rotation itself is `cur = (cur + 1) % 5`; what
 // remains is rebuilding the incoming player's per-state counts with every unit "unmoved".
-CAAA_HD_NOINLINE void rotate_turns(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE void rotate_turns(Game* g, const RunCtx cx) {
   const int nw = (g->cur + 1) % NP;
   g->player = (uint8_t)((g->player + 1) % NP);
   g->cur = (uint8_t)nw;
@@ -1615,6 +1867,7 @@ CAAA_HD_NOINLINE void rotate_turns(Game* g, const RunCtx& cx) {
 #pragma unroll 1
   for (int i = 0; i < (NL * LU_ROW + NS * SU_ROW) / 4; i++) w[i] = 0;
   uint32_t work = 0;
+#pragma unroll 1
   for (int l = 0; l < NL; l++) {
     const uint8_t* mine = utl(g, nw, l);
     uint8_t* row = g->lu[l];
@@ -1628,6 +1881,7 @@ CAAA_HD_NOINLINE void rotate_turns(Game* g, const RunCtx& cx) {
     work |= (f ? W(CAAA_PH_MOVE_FIGHTERS) : 0u) | (b ? W(CAAA_PH_MOVE_BOMBERS) : 0u) | (i ? W(CAAA_PH_MOVE_INFANTRY) : 0u) |
             (a ? W(CAAA_PH_MOVE_ARTILLERY) : 0u) | (tk ? W(CAAA_PH_MOVE_TANKS) : 0u) | (aa ? W(CAAA_PH_MOVE_AA_GUNS) : 0u);
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
     const uint8_t* mine = uts(g, nw, s);
     uint8_t* row = g->su[s];
@@ -1649,12 +1903,14 @@ CAAA_HD_NOINLINE void rotate_turns(Game* g, const RunCtx& cx) {
   g->work = work;
   uint32_t* fl = reinterpret_cast<uint32_t*>(g->flagged);
   fl[0] = fl[1] = 0;
+#pragma unroll 1
   for (int f = 0; f < g->nfact[nw]; f++) {
     const int land = g->factloc[nw][f];
     const uint8_t fm = g->factory_max[land];
     g->builds_left[land] = fm;
-    for (int i = 0; i < cx.T->t.l2s_count[land]; i++) {
-      uint8_t* b = &g->builds_left[cx.T->t.l2s_conn[land][i] + NL];
+#pragma unroll 1
+    for (int i = 0; i < CAAA_TAB(cx)->t.l2s_count[land]; i++) {
+      uint8_t* b = &g->builds_left[CAAA_TAB(cx)->t.l2s_conn[land][i] + NL];
       *b = (uint8_t)(*b + fm);
     }
   }
@@ -1667,7 +1923,7 @@ CAAA_HD constexpr uint32_t cost_byte(int i) { return i < 30 ? cost_land(i % 6) :
 CAAA_HD constexpr uint32_t cost_vec(int w) {
   return cost_byte(4 * w) | (cost_byte(4 * w + 1) << 8) | (cost_byte(4 * w + 2) << 16) | (cost_byte(4 * w + 3) << 24);
 }
-CAAA_HD_NOINLINE double evaluate_state(Game* g, const RunCtx& cx) {
+CAAA_HD_NOINLINE double evaluate_state(Game* g, const RunCtx cx) {
   const uint32_t starting = g->player;
   const int pi = (int)(starting >= (uint32_t)NP ? starting - NP : starting) % NP;
   const int cur = g->cur;
@@ -1689,7 +1945,7 @@ CAAA_HD_NOINLINE double evaluate_state(Game* g, const RunCtx& cx) {
       extra += p < NP - 1 ? uts(g, (pa + 1) % NP, 0)[FIGHTERS] : g->flagged[0];
     }
     score += extra * cost_sea(BOMBERS_SEA);
-    if (cx.T->t.is_allied[pi][(pi + p) % NP]) allied_score += (int)score;
+    if (CAAA_TAB(cx)->t.is_allied[pi][(pi + p) % NP]) allied_score += (int)score;
     else enemy_score += (int)score;
   }
   const double score = (double)allied_score / (double)(enemy_score + allied_score);
@@ -1697,25 +1953,26 @@ CAAA_HD_NOINLINE double evaluate_state(Game* g, const RunCtx& cx) {
 }
 
 // One phase of the pipeline by id (the order is fixed: reference src/engine.cpp:4214-4235).
+// `m` = the lanes of the warp that make this call together (ignored in stop-at-decision mode and on the host)
 template <bool EXPAND>
-CAAA_HD bool run_phase(Game* g, const RunCtx& cx, int ph) {
+CAAA_HD bool run_phase(Game* g, const RunCtx cx, int ph, unsigned m = 0xffffffffu) {
   switch (ph) {
-    case CAAA_PH_MOVE_FIGHTERS: return move_fighter_units<EXPAND>(g, cx);
-    case CAAA_PH_MOVE_BOMBERS: return move_bomber_units<EXPAND>(g, cx);
-    case CAAA_PH_STAGE_TRANSPORTS: return stage_transport_units<EXPAND>(g, cx);
-    case CAAA_PH_MOVE_TANKS: return move_land_unit_type<EXPAND>(g, cx, TANKS, ph);
-    case CAAA_PH_MOVE_ARTILLERY: return move_land_unit_type<EXPAND>(g, cx, ARTILLERY, ph);
-    case CAAA_PH_MOVE_INFANTRY: return move_land_unit_type<EXPAND>(g, cx, INFANTRY, ph);
-    case CAAA_PH_MOVE_TRANSPORTS: return move_transport_units<EXPAND>(g, cx);
-    case CAAA_PH_MOVE_SUBS: return move_subs<EXPAND>(g, cx);
-    case CAAA_PH_MOVE_SHIPS: return move_destroyers_battleships<EXPAND>(g, cx);
-    case CAAA_PH_SEA_BATTLES: return resolve_sea_battles<EXPAND>(g, cx);
-    case CAAA_PH_UNLOAD_TRANSPORTS: return unload_transports<EXPAND>(g, cx);
-    case CAAA_PH_LAND_BATTLES: return resolve_land_battles<EXPAND>(g, cx);
-    case CAAA_PH_MOVE_AA_GUNS: return move_land_unit_type<EXPAND>(g, cx, AA_GUNS, ph);
-    case CAAA_PH_LAND_FIGHTERS: return land_fighter_units<EXPAND>(g, cx);
-    case CAAA_PH_LAND_BOMBERS: return land_bomber_units<EXPAND>(g, cx);
-    case CAAA_PH_BUY_UNITS: return buy_units<EXPAND>(g, cx);
+    case CAAA_PH_MOVE_FIGHTERS: return move_fighter_units<EXPAND>(g, cx, m);
+    case CAAA_PH_MOVE_BOMBERS: return move_bomber_units<EXPAND>(g, cx, m);
+    case CAAA_PH_STAGE_TRANSPORTS: return stage_transport_units<EXPAND>(g, cx, m);
+    case CAAA_PH_MOVE_TANKS: return move_land_unit_type<EXPAND>(g, cx, m, TANKS, ph);
+    case CAAA_PH_MOVE_ARTILLERY: return move_land_unit_type<EXPAND>(g, cx, m, ARTILLERY, ph);
+    case CAAA_PH_MOVE_INFANTRY: return move_land_unit_type<EXPAND>(g, cx, m, INFANTRY, ph);
+    case CAAA_PH_MOVE_TRANSPORTS: return move_transport_units<EXPAND>(g, cx, m);
+    case CAAA_PH_MOVE_SUBS: return move_subs<EXPAND>(g, cx, m);
+    case CAAA_PH_MOVE_SHIPS: return move_destroyers_battleships<EXPAND>(g, cx, m);
+    case CAAA_PH_SEA_BATTLES: return resolve_sea_battles<EXPAND>(g, cx, m);
+    case CAAA_PH_UNLOAD_TRANSPORTS: return unload_transports<EXPAND>(g, cx, m);
+    case CAAA_PH_LAND_BATTLES: return resolve_land_battles<EXPAND>(g, cx, m);
+    case CAAA_PH_MOVE_AA_GUNS: return move_land_unit_type<EXPAND>(g, cx, m, AA_GUNS, ph);
+    case CAAA_PH_LAND_FIGHTERS: return land_fighter_units<EXPAND>(g, cx, m);
+    case CAAA_PH_LAND_BOMBERS: return land_bomber_units<EXPAND>(g, cx, m);
+    case CAAA_PH_BUY_UNITS: return buy_units<EXPAND>(g, cx, m);
     case CAAA_PH_CRASH_AIR: crash_air_units(g, cx); return false;
     case CAAA_PH_RESET_UNITS: reset_units_fully(g); return false;
     case CAAA_PH_BUY_FACTORY: return false;  // buy_factory is empty (3889)
@@ -1725,29 +1982,79 @@ CAAA_HD bool run_phase(Game* g, const RunCtx& cx, int ph) {
   }
 }
 
+// Exact work mask of an arbitrary (imported) state: bit ph is set when phase ph would touch the game.  The
+// pipeline keeps the mask up to date incrementally afterwards; begin_common() may also start from the
+// conservative all-ones mask (every phase then looks once and clears its own bit).
+CAAA_HD uint32_t scan_work(const Game* g) {
+  uint32_t w = 0;
+#pragma unroll 1
+  for (int l = 0; l < NL; l++) {
+    const uint8_t* r = g->lu[l];
+    const uint8_t* f = r + off_lu(FIGHTERS);
+    const uint8_t* b = r + off_lu(BOMBERS_LAND_AIR);
+    if (f[4]) w |= W(CAAA_PH_MOVE_FIGHTERS);
+    if (f[1] | f[2] | f[3]) w |= W(CAAA_PH_LAND_FIGHTERS);
+    if (b[6]) w |= W(CAAA_PH_MOVE_BOMBERS);
+    if (b[1] | b[2] | b[3] | b[4] | b[5]) w |= W(CAAA_PH_LAND_BOMBERS);
+    if (r[off_lu(INFANTRY) + 1]) w |= W(CAAA_PH_MOVE_INFANTRY);
+    if (r[off_lu(ARTILLERY) + 1]) w |= W(CAAA_PH_MOVE_ARTILLERY);
+    if (r[off_lu(TANKS) + 1] | r[off_lu(TANKS) + 2]) w |= W(CAAA_PH_MOVE_TANKS);
+    if (r[off_lu(AA_GUNS) + 1]) w |= W(CAAA_PH_MOVE_AA_GUNS);
+    if (g->flagged[l] != 0) w |= W_LAND_BATTLE;  // units may still arrive before the battle phase
+  }
+#pragma unroll 1
+  for (int s = 0; s < NS; s++) {
+    const uint8_t* r = g->su[s];
+    const uint8_t* f = r + off_sea(FIGHTERS);
+    const uint8_t* b = r + off_sea(BOMBERS_SEA);
+    if (f[4]) w |= W(CAAA_PH_MOVE_FIGHTERS);
+    if (f[1] | f[2] | f[3]) w |= W(CAAA_PH_LAND_FIGHTERS);
+    if (b[0] | b[1] | b[2] | b[3] | b[4]) w |= W(CAAA_PH_LAND_BOMBERS);
+    const uint8_t* e = r + off_sea(TRANS_EMPTY);
+    if (e[3]) w |= W(CAAA_PH_STAGE_TRANSPORTS);
+    if (e[1] | e[2] | e[3]) w |= W(CAAA_PH_MOVE_TRANSPORTS);  // skip_empty_transports
+#pragma unroll 1
+    for (int ut = TRANS_1I; ut <= TRANS_1I_1T; ut++) {
+      const uint8_t* t = r + off_sea(ut);
+      if (ut <= TRANS_1T && t[4]) w |= W(CAAA_PH_STAGE_TRANSPORTS);
+      if (t[2] | t[3]) w |= W(CAAA_PH_MOVE_TRANSPORTS);
+      if (t[1]) w |= W(CAAA_PH_UNLOAD_TRANSPORTS);
+    }
+    if (r[off_sea(SUBMARINES) + 2]) w |= W(CAAA_PH_MOVE_SUBS);
+    if (r[off_sea(DESTROYERS) + 1] | r[off_sea(CARRIERS) + 1] | r[off_sea(CRUISERS) + 2] | r[off_sea(BATTLESHIPS) + 2] |
+        r[off_sea(BS_DAMAGED) + 2])
+      w |= W(CAAA_PH_MOVE_SHIPS);
+    if (g->flagged[s + NL] != 0) w |= W_SEA_BATTLE;
+  }
+  return w;
+}
+
 // Everything a freshly imported state needs before the pipeline can run on it.
-CAAA_HD void begin_common(Game* g, const RunCtx& cx) {
+CAAA_HD void begin_common(Game* g, const RunCtx cx) {
   // entries of the path-blocked tables that no refresh ever writes are read by the flat-index quirk
   // (add_valid_land_moves); they are zero in the reference because its globals are zero-initialised
   g->land_blocked = 0;
   g->seasub_blocked = 0;
+#pragma unroll 1
   for (int p = 0; p < NP; p++)
+#pragma unroll 1
     for (int l = 0; l < NL; l++) g->factloc[p][l] = 0;
   refresh_full_cache(g, cx);
-  g->work = W_ALL_MOVES;  // conservative: every phase looks once and clears its own bit
+  g->work = scan_work(g);
   g->unlucky = 0;
   g->draws = 0;
   g->turns = 0;
   g->status = 0;
 }
 // what random_play_until_terminal does before its loop (4185-4203, with P1 iv and the P2 stream reset)
-CAAA_HD void begin_playout(Game* g, const RunCtx& cx, uint64_t game_id) {
+CAAA_HD void begin_playout(Game* g, const RunCtx cx, uint64_t game_id) {
   begin_common(g, cx);
   g->answers_remaining = 100000;
   g->use_selected = 0;
   g->selected_action = 0;
   g->game_lo = (uint32_t)game_id;
   g->game_hi = (uint32_t)(game_id >> 32);
+#pragma unroll 1
   for (int i = 0; i < CAAA_ACTIONS; i++) g->vm[i] = 0;
   g->nvm = 0;
 }
@@ -1756,6 +2063,7 @@ CAAA_HD uint64_t hash_live_state(const Game* g) {  // FNV-1a-64 over the first 6
   uint8_t buf[CAAA_STATE_BYTES];
   export_state(g, buf);
   uint64_t h = CAAA_FNV_OFFSET;
+#pragma unroll 1
   for (int i = 0; i < CAAA_STATE_LIVE_BYTES; i++) {
     h ^= buf[i];
     h *= CAAA_FNV_PRIME;

@@ -69,6 +69,37 @@ struct RunCtx {
   uint32_t seed_lo, seed_hi;
 };
 
+// The read-only tables: on the device always the CTA's copy at the start of dynamic shared memory (every
+// kernel stages it there first), so the compiler emits shared-memory loads instead of generic ones.
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) uint8_t smem_raw[];
+#endif
+#if defined(__CUDA_ARCH__)
+#define CAAA_TAB(cx) (reinterpret_cast<const DevTables*>(smem_raw))
+#else
+#define CAAA_TAB(cx) ((cx).T)
+#endif
+
+// Warp votes that keep the lanes of a phase loop in lockstep: every lane of `m` stays in the loop until the
+// last one is done, and all of them meet again at the vote at the top of every iteration, so lanes that took
+// different paths through one decision step execute the next one together.  Without the vote a lane that
+// finishes its step early runs ahead and the warp never reconverges.  V = false (stop-at-decision mode, where
+// every lane stops at its own decision, and the host build) degenerates to the plain per-game loop.
+template <bool V>
+CAAA_HD bool vote_any(unsigned m, bool p) {
+#if defined(__CUDA_ARCH__)
+  if (V) return __any_sync(m, p);
+#endif
+  return p;
+}
+template <bool V>
+CAAA_HD unsigned vote_ballot(unsigned m, bool p) {
+#if defined(__CUDA_ARCH__)
+  if (V) return __ballot_sync(m, p);
+#endif
+  return p ? m : 0u;
+}
+
 // ---- accessors ----
 CAAA_HD constexpr uint32_t off_lu(int t) { return off_land(t) - 4u; }
 CAAA_HD uint8_t* lu_ptr(Game* g, int l, int t) { return g->lu[l] + off_lu(t); }
@@ -112,6 +143,7 @@ CAAA_HD uint32_t dot4(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
   return __dp4a(a, b, c);
 #else
+#pragma unroll 1
   for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
   return c;
 #endif
@@ -124,11 +156,14 @@ CAAA_HD void import_state(Game* g, const uint8_t* src) {
   const int player = st->player_index, cur = player % NP;
   g->player = (uint8_t)player;
   g->cur = (uint8_t)cur;
+#pragma unroll 1
   for (int p = 0; p < NP; p++) g->money[(cur + p) % NP] = st->money[p];
+#pragma unroll 1
   for (int a = 0; a < NA; a++) {
     g->builds_left[a] = st->builds_left[a];
     g->flagged[a] = st->flagged_for_combat[a];
   }
+#pragma unroll 1
   for (int l = 0; l < NL; l++) {
     const CaaaLandState& ls = st->land_state[l];
     g->owner[l] = (uint8_t)((ls.owner_idx + cur) % NP);
@@ -136,21 +171,30 @@ CAAA_HD void import_state(Game* g, const uint8_t* src) {
     g->factory_max[l] = ls.factory_max;
     g->bombard_max[l] = ls.bombard_max;
     const uint8_t* u = reinterpret_cast<const uint8_t*>(&ls) + 4;
+#pragma unroll 1
     for (int k = 0; k < LU_ROW; k++) g->lu[l][k] = u[k];
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
     const uint8_t* u = reinterpret_cast<const uint8_t*>(&st->units_sea[s]);
+#pragma unroll 1
     for (int k = 0; k < SU_ROW; k++) g->su[s][k] = u[k];
   }
+#pragma unroll 1
   for (int p = 1; p < NP; p++) {
     const int pa = (cur + p) % NP;
+#pragma unroll 1
     for (int l = 0; l < NL; l++)
+#pragma unroll 1
       for (int u = 0; u < NLT; u++) utl(g, pa, l)[u] = st->other_land_units[p - 1][l][u];
+#pragma unroll 1
     for (int s = 0; s < NS; s++)
+#pragma unroll 1
       for (int u = 0; u < NST - 1; u++) uts(g, pa, s)[u] = st->other_sea_units[p - 1][s][u];
   }
   uint32_t sk0 = 0, sk1 = 0;
   const uint8_t* sm = &st->skipped_moves[0][0];
+#pragma unroll 1
   for (int i = 0; i < 32; i++) {
     sk0 |= (uint32_t)(sm[i] & 1u) << i;
     sk1 |= (uint32_t)(sm[32 + i] & 1u) << i;
@@ -163,11 +207,14 @@ CAAA_HD void export_state(const Game* g, uint8_t* dst) {
   CaaaGameState* st = reinterpret_cast<CaaaGameState*>(dst);
   const int cur = g->cur;
   st->player_index = g->player;
+#pragma unroll 1
   for (int p = 0; p < NP; p++) st->money[p] = g->money[(cur + p) % NP];
+#pragma unroll 1
   for (int a = 0; a < NA; a++) {
     st->builds_left[a] = g->builds_left[a];
     st->flagged_for_combat[a] = g->flagged[a];
   }
+#pragma unroll 1
   for (int l = 0; l < NL; l++) {
     CaaaLandState& ls = st->land_state[l];
     ls.owner_idx = (uint8_t)((g->owner[l] + NP - cur) % NP);
@@ -175,37 +222,50 @@ CAAA_HD void export_state(const Game* g, uint8_t* dst) {
     ls.factory_max = g->factory_max[l];
     ls.bombard_max = g->bombard_max[l];
     uint8_t* u = reinterpret_cast<uint8_t*>(&ls) + 4;
+#pragma unroll 1
     for (int k = 0; k < LU_ROW; k++) u[k] = g->lu[l][k];
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
     uint8_t* u = reinterpret_cast<uint8_t*>(&st->units_sea[s]);
+#pragma unroll 1
     for (int k = 0; k < SU_ROW; k++) u[k] = g->su[s][k];
   }
+#pragma unroll 1
   for (int p = 1; p < NP; p++) {
     const int pa = (cur + p) % NP;
+#pragma unroll 1
     for (int l = 0; l < NL; l++)
+#pragma unroll 1
       for (int u = 0; u < NLT; u++) st->other_land_units[p - 1][l][u] = utl(g, pa, l)[u];
+#pragma unroll 1
     for (int s = 0; s < NS; s++)
+#pragma unroll 1
       for (int u = 0; u < NST - 1; u++) st->other_sea_units[p - 1][s][u] = uts(g, pa, s)[u];
   }
   uint8_t* sm = &st->skipped_moves[0][0];
+#pragma unroll 1
   for (int i = 0; i < 64; i++) sm[i] = (uint8_t)((g->skipped[i >> 5] >> (i & 31)) & 1u);
 }
 
 // the reference's derived globals in the fixed wire layout of CaaaCacheDump (relative player order)
 CAAA_HD void export_cache(const Game* g, const DevTables* T, CaaaCacheDump* d) {
   const int cur = g->cur;
+#pragma unroll 1
   for (int p = 0; p < 6; p++) {
     const int pa = (cur + p) % NP;
     const bool real = p < NP;
     d->income_per_turn[p] = real ? g->income[pa] : 0;
     d->total_factory_count[p] = real ? g->nfact[pa] : 0;
+#pragma unroll 1
     for (int l = 0; l < NL; l++) {
       d->factory_locations[p][l] = real ? g->factloc[pa][l] : 0;
       d->total_player_land_units[p][l] = real ? g->tot_land[pa][l] : 0;
     }
+#pragma unroll 1
     for (int s = 0; s < NS; s++) d->total_player_sea_units[p][s] = real ? g->tot_sea[pa][s] : 0;
   }
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
     d->transports_with_large_cargo_space[s] = g->large_cargo[s];
     d->transports_with_small_cargo_space[s] = g->small_cargo[s];
@@ -213,23 +273,33 @@ CAAA_HD void export_cache(const Game* g, const DevTables* T, CaaaCacheDump* d) {
     d->enemy_blockade_total[s] = g->blockade[s];
     d->enemy_destroyers_total[s] = g->edestroyers[s];
   }
+#pragma unroll 1
   for (int a = 0; a < NA; a++) d->enemy_units_count[a] = g->enemy_count[a];
   d->answers_remaining = g->answers_remaining;
+#pragma unroll 1
   for (int l = 0; l < NL; l++)
+#pragma unroll 1
     for (int u = 0; u < NLT; u++) d->current_player_land_unit_types[l][u] = utl(g, cur, l)[u];
+#pragma unroll 1
   for (int s = 0; s < NS; s++) {
+#pragma unroll 1
     for (int u = 0; u < NST - 1; u++) d->current_player_sea_unit_types[s][u] = uts(g, cur, s)[u];
     d->current_player_sea_unit_types[s][BOMBERS_SEA] = g->cur_sea_bombers[s];
   }
+#pragma unroll 1
   for (unsigned i = 0; i < 25; i++) d->is_land_path_blocked[i] = land_blocked(g, i);
+#pragma unroll 1
   for (unsigned i = 0; i < 9; i++) {
     d->is_sea_path_blocked[i] = sea_blocked(g, i);
     d->is_sub_path_blocked[i] = sub_blocked(g, i);
   }
+#pragma unroll 1
   for (int e = 0; e < 4; e++) d->enemies_0[e] = e < T->n_enemies[cur] ? T->enemies[cur][e] : 0;
+#pragma unroll 1
   for (int p = 0; p < NP; p++) d->is_allied_0[p] = (T->allied_mask[cur] >> p) & 1;
   d->enemies_count_0 = T->n_enemies[cur];
   d->canal_state = g->canal_state;
+#pragma unroll 1
   for (int i = 0; i < CAAA_ACTIONS; i++) d->valid_moves[i] = g->vm[i];
   d->valid_moves_count = g->nvm;
   d->pad_[0] = 0;
