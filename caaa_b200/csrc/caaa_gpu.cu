@@ -52,6 +52,8 @@ struct RolloutArgs {
   CaaaRolloutStats* stats;    // optional
   CaaaBatchSummary* summary;  // optional
   unsigned long long* ticket;
+  int switch_below;
+  int yield_lanes;   // a phase yields when this many of its lanes are done and as many replacements wait (0 = never)
 };
 
 // Import every start / leaf state once: reference layout -> Game with all derived caches, ready to be
@@ -379,7 +381,8 @@ struct Context {
   bool sync_phases = false;  // CAAA_SYNC=1: CTA barrier after every phase (A/B knob)
   bool streaming = true;     // CAAA_ROLLOUT_KERNEL=lockstep selects the walk-the-pipeline kernel instead
   int pool_mult = 3;         // pool entries per shared-memory slot (CAAA_POOL_MULT)
-  int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
+  int lanes = 32;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
+  int group_size = 8;        // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
   void* d_pool = nullptr;    // per-SM game pools of the phase-regrouped kernel
   size_t pool_cap = 0;
 };
@@ -444,27 +447,37 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.stats = d_stats;
   a.summary = d_summary;
   a.ticket = c.d_ticket;
+  {
+    const char* sb = std::getenv("CAAA_SWITCH_BELOW");
+    a.switch_below = sb ? std::atoi(sb) : 16;
+    const char* yl = std::getenv("CAAA_YIELD");
+    a.yield_lanes = yl ? std::atoi(yl) : 0;
+  }
   const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
   const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
   if (c.streaming) {
     const size_t need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game);
-    int rc2 = grow(&c.d_pool, &c.pool_cap, need + sizeof(StreamDbg));
+    const int n_groups = (grid + c.group_size - 1) / c.group_size;
+    const size_t need16 = (need + 15) / 16 * 16;
+    int rc2 = grow(&c.d_pool, &c.pool_cap, need16 + (size_t)n_groups * sizeof(GroupState) + sizeof(StreamDbg));
     if (rc2 != CAAA_OK) return rc2;
+    GroupState* d_groups = (GroupState*)((uint8_t*)c.d_pool + need16);
+    group_init_kernel<<<n_groups, 256, 0, stream>>>(d_groups, n_groups, STREAM_SLOTS * c.pool_mult, c.group_size, grid);
     StreamDbg* d_dbg = nullptr;
     if (std::getenv("CAAA_DEBUG") != nullptr) {
-      d_dbg = (StreamDbg*)((uint8_t*)c.d_pool + need);
+      d_dbg = (StreamDbg*)((uint8_t*)d_groups + (size_t)n_groups * sizeof(GroupState));
       CUDA_TRY(cudaMemsetAsync(d_dbg, 0, sizeof(StreamDbg), stream));
     }
 #define CAAA_LAUNCH_STREAM(L)                                                                                                        \
   do {                                                                                                                              \
     if (d_stats)                                                                                                                    \
-      rollout_kernel_stream<true, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_dbg);  \
+      rollout_kernel_stream<true, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg);  \
     else                                                                                                                            \
-      rollout_kernel_stream<false, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_dbg); \
+      rollout_kernel_stream<false, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
   } while (0)
-    if (c.lanes == 32) CAAA_LAUNCH_STREAM(32);
+    if (c.lanes == 16) CAAA_LAUNCH_STREAM(16);
     else if (c.lanes == 8) CAAA_LAUNCH_STREAM(8);
-    else CAAA_LAUNCH_STREAM(16);
+    else CAAA_LAUNCH_STREAM(32);
     if (d_dbg != nullptr) {
       StreamDbg h;
       cudaStreamSynchronize(stream);
@@ -524,8 +537,12 @@ int caaa_gpu_init(int device) {
   if (c.pool_mult < 1) c.pool_mult = 1;
   if (c.pool_mult > MAX_POOL_MULT) c.pool_mult = MAX_POOL_MULT;
   const char* ln = std::getenv("CAAA_LANES");
-  c.lanes = ln ? std::atoi(ln) : 16;
-  if (c.lanes != 8 && c.lanes != 32) c.lanes = 16;
+  c.lanes = ln ? std::atoi(ln) : 32;
+  if (c.lanes != 8 && c.lanes != 16) c.lanes = 32;
+  const char* gs = std::getenv("CAAA_GROUP");
+  c.group_size = gs ? std::atoi(gs) : 8;
+  if (c.group_size < 1) c.group_size = 1;
+  if (c.group_size > MAX_GROUP) c.group_size = MAX_GROUP;
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));

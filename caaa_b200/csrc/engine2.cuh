@@ -335,16 +335,24 @@ CAAA_HD_NOINLINE uint32_t fighter_landing_masks(Game* g, const RunCtx cx) {  // 
 }
 
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_fighter_units(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int move_fighter_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_FIGHTERS)) != 0);
-  if (!(g->work & W(CAAA_PH_MOVE_FIGHTERS))) return false;
+  if (!(g->work & W(CAAA_PH_MOVE_FIGHTERS))) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   uint32_t masks = 0;
   int src = 0;
+  if (g->cur_phase == CAAA_PH_MOVE_FIGHTERS) {
+    src = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+    masks = g->cur_b;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
 #pragma unroll 1
@@ -415,10 +423,15 @@ CAAA_HD_NOINLINE bool move_fighter_units(Game* g, const RunCtx cx, unsigned min)
     arr[4]--;
     g->work |= W(CAAA_PH_LAND_FIGHTERS);
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_MOVE_FIGHTERS, src, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, masks);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_FIGHTERS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 1: move_bomber_units, 1805-1916, 3423-3443 ----
@@ -430,9 +443,9 @@ CAAA_HD uint32_t bomber_here_mask(const Game* g, const RunCtx cx) {  // 1808-181
   return here;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int move_bomber_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m0 = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_BOMBERS)) != 0);
-  if (!(g->work & W(CAAA_PH_MOVE_BOMBERS))) return false;
+  if (!(g->work & W(CAAA_PH_MOVE_BOMBERS))) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   // the landing masks are phase-local here (the reference keeps them in globals, but re-derives them
@@ -443,29 +456,39 @@ CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx cx, unsigned min) 
   const unsigned m = vote_ballot<!EXPAND>(m0, any);
   if (!any) {
     g->work &= ~W(CAAA_PH_MOVE_BOMBERS);
-    return false;
+    return PH_DONE;
   }
-  const uint32_t here = bomber_here_mask(g, cx);
-  uint32_t in1 = 0, in2 = 0;
-#pragma unroll 1
-  for (int l = 0; l < NL; l++)
-#pragma unroll 1
-    for (int i = 0; i < t.l2l_count[l]; i++)
-      if ((here >> t.l2l_conn[l][i]) & 1) { in1 |= 1u << l; break; }
-#pragma unroll 1
-  for (int s = 0; s < NS; s++)
-#pragma unroll 1
-    for (int i = 0; i < t.s2l_count[s]; i++)
-      if ((here >> t.s2l_conn[s][i]) & 1) { in1 |= 1u << (NL + s); break; }
-#pragma unroll 1
-  for (int a = 0; a < NA; a++)
-#pragma unroll 1
-    for (int i = 0; i < t.air_conn_count[a]; i++)
-      if ((in1 >> t.air_conn[a][i]) & 1) { in2 |= 1u << a; break; }
+  uint32_t here = 0, in1 = 0, in2 = 0;
   bool fresh = true;
   int src = 0;
+  if (g->cur_phase == CAAA_PH_MOVE_BOMBERS) {
+    src = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    here = g->cur_b & 0xffu;
+    in1 = (g->cur_b >> 8) & 0xffu;
+    in2 = (g->cur_b >> 16) & 0xffu;
+  } else {
+    here = bomber_here_mask(g, cx);
+  #pragma unroll 1
+    for (int l = 0; l < NL; l++)
+  #pragma unroll 1
+      for (int i = 0; i < t.l2l_count[l]; i++)
+        if ((here >> t.l2l_conn[l][i]) & 1) { in1 |= 1u << l; break; }
+  #pragma unroll 1
+    for (int s = 0; s < NS; s++)
+  #pragma unroll 1
+      for (int i = 0; i < t.s2l_count[s]; i++)
+        if ((here >> t.s2l_conn[s][i]) & 1) { in1 |= 1u << (NL + s); break; }
+  #pragma unroll 1
+    for (int a = 0; a < NA; a++)
+  #pragma unroll 1
+      for (int i = 0; i < t.air_conn_count[a]; i++)
+        if ((in1 >> t.air_conn[a][i]) & 1) { in2 |= 1u << a; break; }
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
 #pragma unroll 1
@@ -527,22 +550,34 @@ CAAA_HD_NOINLINE bool move_bomber_units(Game* g, const RunCtx cx, unsigned min) 
     arr[6]--;
     g->work |= W(CAAA_PH_LAND_BOMBERS);
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_MOVE_BOMBERS, src, fresh ? CF_FRESH : 0u, 0u, here | (in1 << 8) | (in2 << 16));
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_BOMBERS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 2: stage_transport_units, 1588-1655 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int stage_transport_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_STAGE_TRANSPORTS)) != 0);
-  if (!(g->work & W(CAAA_PH_STAGE_TRANSPORTS))) return false;
+  if (!(g->work & W(CAAA_PH_STAGE_TRANSPORTS))) return PH_DONE;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int cell = 0;  // (ut - TRANS_EMPTY) * NS + sea, in the reference's loop order
+  if (g->cur_phase == CAAA_PH_STAGE_TRANSPORTS) {
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0, staging = 0;
@@ -603,24 +638,36 @@ CAAA_HD_NOINLINE bool stage_transport_units(Game* g, const RunCtx cx, unsigned m
       g->large_cargo[ds]++;
     }
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_STAGE_TRANSPORTS, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, 0u);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_STAGE_TRANSPORTS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phases 3,4,5,12: move_land_unit_type, 1986-2060 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx cx, unsigned min, int ut, int ph) {
+CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min, int ut, int ph, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(ph)) != 0);
-  if (!(g->work & W(ph))) return false;
+  if (!(g->work & W(ph))) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   const int mm = max_move_land(ut);
   bool processed = false, fresh = true;
   int cell = 0;  // src * mm + (mm - moves)
+  if (g->cur_phase == ph) {
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
     int src = 0, moves = 0;
@@ -685,18 +732,24 @@ CAAA_HD_NOINLINE bool move_land_unit_type(Game* g, const RunCtx cx, unsigned min
       flag_combat(g, dst, 2);
     }
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, ph, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, 0u);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(ph);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 6: move_transport_units, 2062-2159 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int move_transport_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_TRANSPORTS)) != 0);
-  if (!(g->work & W(CAAA_PH_MOVE_TRANSPORTS))) return false;
+  if (!(g->work & W(CAAA_PH_MOVE_TRANSPORTS))) return PH_DONE;
   const int cur = g->cur;
+  if (g->cur_phase != CAAA_PH_MOVE_TRANSPORTS)
 #pragma unroll 1
   for (int s = 0; s < NS; s++) {  // skip_empty_transports 2062-2075
     uint8_t* e = su_ptr(g, s, TRANS_EMPTY);
@@ -708,8 +761,15 @@ CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx cx, unsigned mi
   }
   bool processed = false, fresh = true;
   int cell = 0;  // ((ut - TRANS_1I) * NS + sea) * 2 + (i - 1); every loaded type has max_state 4
+  if (g->cur_phase == CAAA_PH_MOVE_TRANSPORTS) {
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0, cs = 0;
@@ -766,22 +826,34 @@ CAAA_HD_NOINLINE bool move_transport_units(Game* g, const RunCtx cx, unsigned mi
       }
     }
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_MOVE_TRANSPORTS, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, 0u);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_TRANSPORTS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 7: move_subs, 2160-2214 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_subs(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int move_subs(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_SUBS)) != 0);
-  if (!(g->work & W(CAAA_PH_MOVE_SUBS))) return false;
+  if (!(g->work & W(CAAA_PH_MOVE_SUBS))) return PH_DONE;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int s = 0;
+  if (g->cur_phase == CAAA_PH_MOVE_SUBS) {
+    s = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
 #pragma unroll 1
@@ -825,10 +897,15 @@ CAAA_HD_NOINLINE bool move_subs(Game* g, const RunCtx cx, unsigned min) {
     uts(g, cur, s)[SUBMARINES]--;
     g->tot_sea[cur][s]--;
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_MOVE_SUBS, s, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, 0u);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_SUBS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 8: move_destroyers_battleships, 2216-2310 ----
@@ -850,14 +927,21 @@ CAAA_HD void carry_allied_fighters(Game* g, const RunCtx cx, int src, int dst) {
   }
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool move_destroyers_battleships(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int move_destroyers_battleships(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_MOVE_SHIPS)) != 0);
-  if (!(g->work & W(CAAA_PH_MOVE_SHIPS))) return false;
+  if (!(g->work & W(CAAA_PH_MOVE_SHIPS))) return PH_DONE;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int cell = 0;  // (ut - DESTROYERS) * NS + sea
+  if (g->cur_phase == CAAA_PH_MOVE_SHIPS) {
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0, unmoved = 0;
@@ -907,10 +991,15 @@ CAAA_HD_NOINLINE bool move_destroyers_battleships(Game* g, const RunCtx cx, unsi
     g->tot_sea[cur][s]--;
     if (ut == CARRIERS) carry_allied_fighters(g, cx, s, ds);
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_MOVE_SHIPS, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, 0u);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_MOVE_SHIPS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- casualty removal ----
@@ -1089,16 +1178,24 @@ CAAA_HD void sea_retreat(Game* g, int src, int dst) {  // 2582-2603
   g->flagged[src + NL] = 0;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int resolve_sea_battles(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W_SEA_BATTLE) != 0);
-  if (!(g->work & W_SEA_BATTLE)) return false;
+  if (!(g->work & W_SEA_BATTLE)) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur, ne = CAAA_TAB(cx)->n_enemies[cur];
   const uint8_t* en = CAAA_TAB(cx)->enemies_abs[cur];
   int s = 0, rounds = 0;
   bool in_battle = false, submerged = false;
+  if (g->cur_phase == CAAA_PH_SEA_BATTLES) {
+    s = g->cur_cell;
+    in_battle = (g->cur_flags & CF_IN_BATTLE) != 0;
+    submerged = (g->cur_flags & CF_SUBMERGED) != 0;
+    rounds = (int)g->cur_b;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     if (!in_battle) {  // next flagged sea with own units (one sea per iteration keeps the lanes together)
 #pragma unroll 1
@@ -1243,22 +1340,34 @@ CAAA_HD_NOINLINE bool resolve_sea_battles(Game* g, const RunCtx cx, unsigned min
       s++;
     }
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_SEA_BATTLES, s, (in_battle ? CF_IN_BATTLE : 0u) | (submerged ? CF_SUBMERGED : 0u), 0u, (uint32_t)rounds);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   g->work &= ~W_SEA_BATTLE;
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 10: unload_transports, 2984-3053, 3373-3383 ----
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int unload_transports(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_UNLOAD_TRANSPORTS)) != 0);
-  if (!(g->work & W(CAAA_PH_UNLOAD_TRANSPORTS))) return false;
+  if (!(g->work & W(CAAA_PH_UNLOAD_TRANSPORTS))) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   int cell = 0;  // (ut - TRANS_1I) * NS + sea
+  if (g->cur_phase == CAAA_PH_UNLOAD_TRANSPORTS) {
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
     int ut = 0, s = 0;
@@ -1322,10 +1431,15 @@ CAAA_HD_NOINLINE bool unload_transports(Game* g, const RunCtx cx, unsigned min) 
       if (g->enemy_count[dst] == 0) conquer_land(g, cx, dst);
     }
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_UNLOAD_TRANSPORTS, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, 0u);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_UNLOAD_TRANSPORTS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 11: resolve_land_battles, 3055-3371 ----
@@ -1345,17 +1459,24 @@ CAAA_HD void hit_air_states(Game* g, int land, int ut, int lo, int hi, uint32_t&
   }
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int resolve_land_battles(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W_LAND_BATTLE) != 0);
-  if (!(g->work & W_LAND_BATTLE)) return false;
+  if (!(g->work & W_LAND_BATTLE)) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur, ne = CAAA_TAB(cx)->n_enemies[cur];
   const uint8_t* en = CAAA_TAB(cx)->enemies_abs[cur];
   int l = 0;
   uint32_t rounds = 0;
   bool in_battle = false;
+  if (g->cur_phase == CAAA_PH_LAND_BATTLES) {
+    l = g->cur_cell;
+    in_battle = (g->cur_flags & CF_IN_BATTLE) != 0;
+    rounds = g->cur_b;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     if (!in_battle) {
 #pragma unroll 1
@@ -1492,9 +1613,14 @@ CAAA_HD_NOINLINE bool resolve_land_battles(Game* g, const RunCtx cx, unsigned mi
       l++;
     }
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_LAND_BATTLES, l, in_battle ? CF_IN_BATTLE : 0u, 0u, rounds);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   g->work &= ~W_LAND_BATTLE;
-  return false;
+  return PH_DONE;
 }
 
 // ---- phases 13/14: land_fighter_units / land_bomber_units, 3409-3421, 3445-3654 ----
@@ -1514,16 +1640,24 @@ CAAA_HD uint32_t fighter_final_landing_mask(Game* g, const RunCtx cx) {  // refr
   return here;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int land_fighter_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_LAND_FIGHTERS)) != 0);
-  if (!(g->work & W(CAAA_PH_LAND_FIGHTERS))) return false;
+  if (!(g->work & W(CAAA_PH_LAND_FIGHTERS))) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   uint32_t here = 0;
   int cell = 0;  // (state - 1) * NA + src
+  if (g->cur_phase == CAAA_PH_LAND_FIGHTERS) {
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+    here = g->cur_b;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
     int src = 0, cs = 0;
@@ -1585,22 +1719,35 @@ CAAA_HD_NOINLINE bool land_fighter_units(Game* g, const RunCtx cx, unsigned min)
     }
     arr[cs]--;
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_LAND_FIGHTERS, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, here);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_LAND_FIGHTERS);
-  return false;
+  return PH_DONE;
 }
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int land_bomber_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(CAAA_PH_LAND_BOMBERS)) != 0);
-  if (!(g->work & W(CAAA_PH_LAND_BOMBERS))) return false;
+  if (!(g->work & W(CAAA_PH_LAND_BOMBERS))) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   bool processed = false, fresh = true;
   uint32_t here = 0;
   int cell = 0;  // cur1 * NA + src
+  if (g->cur_phase == CAAA_PH_LAND_BOMBERS) {
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+    here = g->cur_b;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
     int src = 0, cs = 0;
@@ -1659,25 +1806,41 @@ CAAA_HD_NOINLINE bool land_bomber_units(Game* g, const RunCtx cx, unsigned min) 
     }
     arr[cs]--;
   }
-  if (stop) return true;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_LAND_BOMBERS, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, here);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
   if (processed) clear_move_history(g);
   g->work &= ~W(CAAA_PH_LAND_BOMBERS);
-  return false;
+  return PH_DONE;
 }
 
 // ---- phase 15: buy_units (purchase and placement), 3663-3834 ----
 // One flat loop: a cell is (factory, adjacent sea) or (factory, the land itself); every iteration is one
 // purchase decision of the cell the lane is at.
 template <bool EXPAND>
-CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx cx, unsigned min) {
+CAAA_HD_NOINLINE int buy_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
   const unsigned m = min;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   int f = 0, si = 0;
   bool new_factory = true, new_cell = true, processed = false;
   uint32_t repair = 0, last = 0;
+  if (g->cur_phase == CAAA_PH_BUY_UNITS) {
+    f = g->cur_cell;
+    si = g->cur_a;
+    new_factory = (g->cur_flags & CF_NEW_FACTORY) != 0;
+    new_cell = (g->cur_flags & CF_NEW_CELL) != 0;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+    repair = g->cur_b & 0xffu;
+    last = (g->cur_b >> 8) & 0xffu;
+  }
   bool active = true, stop = false;
+  int steps = 0;
   while (vote_any<!EXPAND>(m, active)) {
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     if (f >= g->nfact[cur]) {
       active = false;
@@ -1800,7 +1963,14 @@ CAAA_HD_NOINLINE bool buy_units(Game* g, const RunCtx cx, unsigned min) {
       }
     }
   }
-  return stop;
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, CAAA_PH_BUY_UNITS, f, (new_factory ? CF_NEW_FACTORY : 0u) | (new_cell ? CF_NEW_CELL : 0u) | (processed ? CF_PROCESSED : 0u),
+                (uint32_t)si, repair | (last << 8));
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
+  return PH_DONE;
 }
 
 // ---- phases 16-19: crash_air_units, reset_units_fully, collect_money, 3836-3894 ----
@@ -1955,30 +2125,30 @@ CAAA_HD_NOINLINE double evaluate_state(Game* g, const RunCtx cx) {
 // One phase of the pipeline by id (the order is fixed: reference src/engine.cpp:4214-4235).
 // `m` = the lanes of the warp that make this call together (ignored in stop-at-decision mode and on the host)
 template <bool EXPAND>
-CAAA_HD bool run_phase(Game* g, const RunCtx cx, int ph, unsigned m = 0xffffffffu) {
+CAAA_HD int run_phase(Game* g, const RunCtx cx, int ph, unsigned m = 0xffffffffu, int yield = 0) {
   switch (ph) {
-    case CAAA_PH_MOVE_FIGHTERS: return move_fighter_units<EXPAND>(g, cx, m);
-    case CAAA_PH_MOVE_BOMBERS: return move_bomber_units<EXPAND>(g, cx, m);
-    case CAAA_PH_STAGE_TRANSPORTS: return stage_transport_units<EXPAND>(g, cx, m);
-    case CAAA_PH_MOVE_TANKS: return move_land_unit_type<EXPAND>(g, cx, m, TANKS, ph);
-    case CAAA_PH_MOVE_ARTILLERY: return move_land_unit_type<EXPAND>(g, cx, m, ARTILLERY, ph);
-    case CAAA_PH_MOVE_INFANTRY: return move_land_unit_type<EXPAND>(g, cx, m, INFANTRY, ph);
-    case CAAA_PH_MOVE_TRANSPORTS: return move_transport_units<EXPAND>(g, cx, m);
-    case CAAA_PH_MOVE_SUBS: return move_subs<EXPAND>(g, cx, m);
-    case CAAA_PH_MOVE_SHIPS: return move_destroyers_battleships<EXPAND>(g, cx, m);
-    case CAAA_PH_SEA_BATTLES: return resolve_sea_battles<EXPAND>(g, cx, m);
-    case CAAA_PH_UNLOAD_TRANSPORTS: return unload_transports<EXPAND>(g, cx, m);
-    case CAAA_PH_LAND_BATTLES: return resolve_land_battles<EXPAND>(g, cx, m);
-    case CAAA_PH_MOVE_AA_GUNS: return move_land_unit_type<EXPAND>(g, cx, m, AA_GUNS, ph);
-    case CAAA_PH_LAND_FIGHTERS: return land_fighter_units<EXPAND>(g, cx, m);
-    case CAAA_PH_LAND_BOMBERS: return land_bomber_units<EXPAND>(g, cx, m);
-    case CAAA_PH_BUY_UNITS: return buy_units<EXPAND>(g, cx, m);
-    case CAAA_PH_CRASH_AIR: crash_air_units(g, cx); return false;
-    case CAAA_PH_RESET_UNITS: reset_units_fully(g); return false;
-    case CAAA_PH_BUY_FACTORY: return false;  // buy_factory is empty (3889)
-    case CAAA_PH_COLLECT_MONEY: collect_money(g, cx); return false;
-    case CAAA_PH_ROTATE_TURNS: rotate_turns(g, cx); return false;
-    default: return false;
+    case CAAA_PH_MOVE_FIGHTERS: return move_fighter_units<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_MOVE_BOMBERS: return move_bomber_units<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_STAGE_TRANSPORTS: return stage_transport_units<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_MOVE_TANKS: return move_land_unit_type<EXPAND>(g, cx, m, TANKS, ph, yield);
+    case CAAA_PH_MOVE_ARTILLERY: return move_land_unit_type<EXPAND>(g, cx, m, ARTILLERY, ph, yield);
+    case CAAA_PH_MOVE_INFANTRY: return move_land_unit_type<EXPAND>(g, cx, m, INFANTRY, ph, yield);
+    case CAAA_PH_MOVE_TRANSPORTS: return move_transport_units<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_MOVE_SUBS: return move_subs<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_MOVE_SHIPS: return move_destroyers_battleships<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_SEA_BATTLES: return resolve_sea_battles<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_UNLOAD_TRANSPORTS: return unload_transports<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_LAND_BATTLES: return resolve_land_battles<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_MOVE_AA_GUNS: return move_land_unit_type<EXPAND>(g, cx, m, AA_GUNS, ph, yield);
+    case CAAA_PH_LAND_FIGHTERS: return land_fighter_units<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_LAND_BOMBERS: return land_bomber_units<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_BUY_UNITS: return buy_units<EXPAND>(g, cx, m, yield);
+    case CAAA_PH_CRASH_AIR: crash_air_units(g, cx); return PH_DONE;
+    case CAAA_PH_RESET_UNITS: reset_units_fully(g); return PH_DONE;
+    case CAAA_PH_BUY_FACTORY: return PH_DONE;  // buy_factory is empty (3889)
+    case CAAA_PH_COLLECT_MONEY: collect_money(g, cx); return PH_DONE;
+    case CAAA_PH_ROTATE_TURNS: rotate_turns(g, cx); return PH_DONE;
+    default: return PH_DONE;
   }
 }
 
@@ -2041,6 +2211,7 @@ CAAA_HD void begin_common(Game* g, const RunCtx cx) {
     for (int l = 0; l < NL; l++) g->factloc[p][l] = 0;
   refresh_full_cache(g, cx);
   g->work = scan_work(g);
+  g->cur_phase = CUR_NONE;
   g->unlucky = 0;
   g->draws = 0;
   g->turns = 0;

@@ -7,7 +7,7 @@
 // never rotates; "relative player p" of the reference is absolute player (cur + p) % 5.  The
 // reference layout only exists at the ABI: import_state() / export_state() convert.
 //
-// Layout rules: 924 bytes = 231 words (odd, so the 32 lanes of a warp touching the same field of 32
+// Layout rules: 932 bytes = 233 words (odd, so the 32 lanes of a warp touching the same field of 32
 // games hit 32 different banks); every array that is scanned word-wise starts on a word boundary;
 // per-player unit totals are one 72-byte vector per player (30 land + 42 sea counts) so that scoring
 // is 18 dp4a per player against a constant cost vector.
@@ -58,8 +58,12 @@ struct Game {
   uint8_t canal_state;
   uint8_t use_selected, selected_action, unlucky;  // expansion mode (src/engine.cpp:156,160,163)
   uint8_t pad_[1];
+  // loop cursor of a phase that yielded before it was done (phase-regrouped kernel): lets the phase resume
+  // exactly where it stopped, with its valid-moves list (vm/nvm above) and its per-phase masks intact
+  uint8_t cur_phase, cur_cell, cur_flags, cur_a;
+  uint32_t cur_b;
 };
-static_assert(sizeof(Game) == 924, "Game layout");
+static_assert(sizeof(Game) == 932, "Game layout");
 static_assert((sizeof(Game) / 4) % 2 == 1, "slot stride must be an odd number of words");
 static_assert(offsetof(Game, ut) % 4 == 0 && offsetof(Game, lu) % 4 == 0 && offsetof(Game, flagged) % 4 == 0, "word alignment");
 static_assert((NL * LU_ROW + NS * SU_ROW) % 4 == 0, "per-state counts are cleared word-wise");
@@ -98,6 +102,30 @@ CAAA_HD unsigned vote_ballot(unsigned m, bool p) {
   if (V) return __ballot_sync(m, p);
 #endif
   return p ? m : 0u;
+}
+
+constexpr uint8_t CUR_NONE = 0xff;
+constexpr uint32_t CF_FRESH = 1, CF_PROCESSED = 2, CF_IN_BATTLE = 4, CF_SUBMERGED = 8, CF_NEW_FACTORY = 16, CF_NEW_CELL = 32;
+CAAA_HD void save_cursor(Game* g, int ph, int cell, uint32_t flags, uint32_t a, uint32_t b) {
+  g->cur_phase = (uint8_t)ph;
+  g->cur_cell = (uint8_t)cell;
+  g->cur_flags = (uint8_t)flags;
+  g->cur_a = (uint8_t)a;
+  g->cur_b = b;
+}
+// Phase results: 0 = ran to completion, 1 = stopped at a decision (stop-at-decision mode, or the decision
+// budget of a rollout is exhausted), 2 = yielded with its cursor saved (call again to continue).
+constexpr int PH_DONE = 0, PH_STOPPED = 1, PH_YIELDED = 2;
+// A lockstep loop yields when `yield` of its lanes have finished (device; 0 = never), so that the caller can
+// replace them with other games waiting for the same phase instead of idling them until the slowest lane is
+// done.  On the host (tests) `yield` is a plain budget of loop iterations.
+template <bool V>
+CAAA_HD bool should_yield(unsigned m, bool active, int yield, int& steps) {
+  if (yield <= 0) return false;
+#if defined(__CUDA_ARCH__)
+  if (V) return __popc(__ballot_sync(m, !active)) >= yield;
+#endif
+  return steps++ >= yield;
 }
 
 // ---- accessors ----

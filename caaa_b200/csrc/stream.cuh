@@ -23,21 +23,48 @@
 
 namespace caaa {
 
-constexpr int NQ = 17;                   // phases 0..14, 15 = end of turn, 16 = free pool entries
-constexpr int Q_EOT = CAAA_PH_BUY_UNITS; // 15
+constexpr int NQ = 17;                   // phases 0..14, 15 = end of turn (purchase, bookkeeping, rotation, scoring,
+constexpr int Q_EOT = CAAA_PH_BUY_UNITS; // finish + restart), 16 = free pool entries
 constexpr int Q_FREE = 16;
 constexpr int STREAM_SLOTS = 224;        // shared-memory game slots per CTA
 constexpr int MAX_POOL_MULT = 4;
 constexpr int MAX_BM_WORDS = STREAM_SLOTS * MAX_POOL_MULT / 32;  // 28 bitmap words per phase
 
+constexpr int MAX_GROUP = 16;            // SMs that share one pool and one set of phase bitmaps
+constexpr int MAX_BM_WORDS_G = MAX_BM_WORDS * MAX_GROUP;
+
+// One per group of CTAs, in global memory (L2): the CTAs of a group pool their games, so that a CTA finds
+// enough games waiting for ONE phase to keep all of its warps in that phase's code.
+struct GroupState {
+  uint32_t bm[NQ][MAX_BM_WORDS_G];  // pool entries waiting per phase
+  int cnt[NQ];                      // their number (selection heuristic; the bitmaps are the truth)
+  int servers[NQ];                  // CTAs currently serving each phase
+  int retired;                      // pool entries that found no ticket left
+  int pad_[3];
+};
 struct StreamShared {
-  uint32_t bm[NQ][MAX_BM_WORDS];  // pool entries waiting per phase
-  int cnt[NQ];                    // their number (selection heuristic; the bitmaps are the truth)
-  int kind;                       // the phase this CTA currently prefers
-  int retired;                    // pool entries that found no ticket left
+  int kind;                       // the phase this CTA currently serves
   uint16_t batch[STREAM_SLOTS];   // claimed entries, LANES per warp
+  uint8_t target[STREAM_SLOTS];   // the slot (lane) each claimed entry goes to
 };
 constexpr int STREAM_SMEM = TABLE_BYTES + STREAM_SLOTS * (int)sizeof(Game) + (int)((sizeof(StreamShared) + 15) / 16 * 16);
+
+__global__ void group_init_kernel(GroupState* G, int n_groups, int entries_per_cta, int group_size, int grid) {
+  GroupState* gs = G + blockIdx.x;
+  if ((int)blockIdx.x >= n_groups) return;
+  const int first = (int)blockIdx.x * group_size;
+  const int pool_g = entries_per_cta * ((grid - first) < group_size ? (grid - first) : group_size);
+  const int words = pool_g / 32;
+  for (int i = threadIdx.x; i < NQ * MAX_BM_WORDS_G; i += blockDim.x) {
+    const int q = i / MAX_BM_WORDS_G, w = i % MAX_BM_WORDS_G;
+    gs->bm[q][w] = (q == Q_FREE && w < words) ? 0xffffffffu : 0u;
+  }
+  if (threadIdx.x < NQ) {
+    gs->cnt[threadIdx.x] = threadIdx.x == Q_FREE ? pool_g : 0;
+    gs->servers[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0) gs->retired = 0;
+}
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -49,34 +76,38 @@ struct StreamDbg {
   unsigned long long batches, items, t[6];
 };
 
-// LANES = games per warp.  The kernel is bound by per-warp latency, not by issue slots, and a batch rarely
-// fills 32 lanes with equally long work, so fewer games per warp and more warps per SM (224 / LANES) is the
-// better trade: more independent instruction streams to hide latency, a shorter wait for the slowest lane.
+// LANES = games per warp.  A warp serves ONE phase at a time: it claims games waiting for that phase, runs the
+// phase on them in lockstep, and -- because the work per game is heavy-tailed -- lets the phase YIELD as soon as a
+// quarter of its lanes are done: the finished games are routed on, their lanes are refilled with other games
+// waiting for the same phase, and the unfinished games simply resume from the cursor saved in the game
+// (engine2.cuh), without leaving shared memory.
 template <bool STATS, int LANES>
 __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_stream(const RolloutArgs a, uint32_t* pool_all, int pool_mult,
-                                                                                       StreamDbg* dbg) {
+                                                                                       GroupState* groups, int group_size, StreamDbg* dbg) {
   const DevTables* T = stage_tables(a.tables);
   StreamShared* S = reinterpret_cast<StreamShared*>(smem_raw + TABLE_BYTES + STREAM_SLOTS * sizeof(Game));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pool_n = STREAM_SLOTS * pool_mult, bm_words = pool_n / 32;
-  uint32_t* const pool = pool_all + (size_t)blockIdx.x * pool_n * GAME_WORDS;
-  for (int i = threadIdx.x; i < NQ * MAX_BM_WORDS; i += blockDim.x) {
-    const int q = i / MAX_BM_WORDS, w = i % MAX_BM_WORDS;
-    S->bm[q][w] = (q == Q_FREE && w < bm_words) ? 0xffffffffu : 0u;
-  }
-  if (threadIdx.x < NQ) S->cnt[threadIdx.x] = threadIdx.x == Q_FREE ? pool_n : 0;
-  if (threadIdx.x == 0) {
-    S->kind = Q_FREE;
-    S->retired = 0;
-  }
+  const int group = blockIdx.x / group_size;
+  const int first_cta = group * group_size;
+  const int ctas_here = ((int)gridDim.x - first_cta) < group_size ? ((int)gridDim.x - first_cta) : group_size;
+  const int pool_n = STREAM_SLOTS * pool_mult * ctas_here, bm_words = pool_n / 32;
+  GroupState* const GS = groups + group;
+  uint32_t* const pool = pool_all + (size_t)first_cta * STREAM_SLOTS * pool_mult * GAME_WORDS;
+  if (threadIdx.x == 0) S->kind = -1;
   __syncthreads();
   Game* const warp_games = reinterpret_cast<Game*>(smem_raw + TABLE_BYTES) + warp * LANES;
   Game* const g = warp_games + (lane < LANES ? lane : 0);
+  uint16_t* const batch = S->batch + warp * LANES;
   const RunCtx cx{T, (uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
   const bool one_state = a.rollouts_per_state >= a.n_games;
-  volatile int* vcnt = S->cnt;
+  volatile int* vcnt = GS->cnt;
+  volatile int* vsrv = GS->servers;
   volatile int* vkind = &S->kind;
-  volatile int* vretired = &S->retired;
+  volatile int* vretired = &GS->retired;
+  unsigned scan_rot = (unsigned)(blockIdx.x * 7 + warp * 3);  // where this warp starts scanning the bitmaps
+  const int switch_below = a.switch_below;  // leave a phase when fewer entries than this wait for it
+  constexpr unsigned LANE_MASK = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
+  constexpr int KW = (GAME_WORDS + 31) / 32;
   LaneTotals tot;
   unsigned long long d_batches = 0, d_items = 0, d_t[6] = {0, 0, 0, 0, 0, 0};
   long long d_c0 = clock64();
@@ -89,187 +120,246 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
     }                                                 \
   } while (0)
 
+  // claim up to `want` entries waiting for `kind` into batch[]; each lane takes bits of one bitmap word per round
+  auto claim = [&](int kind, int want) -> int {
+    int n = 0;
+    const int rounds = (bm_words + 31) / 32;
+    for (int r = 0; r < rounds && n < want; r++) {
+      const int wi = (int)((scan_rot + (unsigned)(r * 32 + lane)) % (unsigned)(rounds * 32));
+      uint32_t word = wi < bm_words ? *reinterpret_cast<volatile uint32_t*>(&GS->bm[kind][wi]) : 0u;
+      if (!__any_sync(FULL, word != 0)) continue;
+      int pc = __popc(word), incl = pc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int allow = want - n - (incl - pc);
+      allow = allow < 0 ? 0 : (allow > pc ? pc : allow);
+      while (__popc(word) > allow) word &= ~(0x80000000u >> __clz(word));  // keep the lowest `allow` bits
+      uint32_t claimed = word ? (atomicAnd(&GS->bm[kind][wi], ~word) & word) : 0u;
+      pc = __popc(claimed);
+      incl = pc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int o = n + incl - pc;
+      while (claimed) {
+        const int b = __ffs(claimed) - 1;
+        claimed &= claimed - 1;
+        batch[o++] = (uint16_t)(wi * 32 + b);
+      }
+      n += __shfl_sync(FULL, incl, 31);
+    }
+    scan_rot += 32;
+    if (n > 0 && lane == 0) atomicSub(&GS->cnt[kind], n);
+    __syncwarp();
+    return n;
+  };
+
   for (;;) {
-    // ---- choose a phase: the CTA's current one while it can fill most of a warp, else the fullest ----
+    // ---- choose a phase: the CTA's current one while enough entries wait for it, else the one with the most
+    // entries per serving CTA (ties go to the later phase, which is closer to finishing a turn) ----
     const int c = lane < NQ ? vcnt[lane] : 0;
     int kind = *vkind;
-    int c_kind = __shfl_sync(FULL, c, kind);
-    if (c_kind <= 0) {
-      // fullest bitmap; ties go to the later phase, which is closer to finishing a turn
-      const unsigned key = __reduce_max_sync(FULL, c > 0 ? ((unsigned)c << 5) | (unsigned)lane : 0u);
+    if (kind < 0 || __shfl_sync(FULL, c, kind) < switch_below) {
+      const int srv = lane < NQ ? vsrv[lane] - (lane == kind ? 1 : 0) : 0;
+      const unsigned score = c > 0 ? (unsigned)((c << 4) / (srv + 1)) + 1u : 0u;
+      const unsigned key = __reduce_max_sync(FULL, score ? (score << 5) | (unsigned)lane : 0u);
       if (key == 0) {
         if (*vretired >= pool_n) break;  // every pool entry has retired: the batch is done
         __nanosleep(200);
         continue;
       }
-      kind = (int)(key & 31u);
-      c_kind = (int)(key >> 5);
-      if (lane == 0) *vkind = kind;
-    }
-    // share the waiting entries between the warps of the CTA, so that they all serve this phase at the same time
-    constexpr int WARPS = STREAM_SLOTS / LANES;
-    int take = (c_kind + WARPS - 1) / WARPS;
-    take = take < 1 ? 1 : (take > LANES ? LANES : take);
-    // ---- claim up to LANES waiting entries: lane w takes bits of bitmap word w ----
-    uint32_t word = lane < bm_words ? *reinterpret_cast<volatile uint32_t*>(&S->bm[kind][lane]) : 0u;
-    int pc = __popc(word), incl = pc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    int allow = take - (incl - pc);
-    allow = allow < 0 ? 0 : (allow > pc ? pc : allow);
-    while (__popc(word) > allow) word &= ~(0x80000000u >> __clz(word));  // keep the lowest `allow` bits
-    uint32_t claimed = word ? (atomicAnd(&S->bm[kind][lane], ~word) & word) : 0u;
-    pc = __popc(claimed);
-    incl = pc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(FULL, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int n = __shfl_sync(FULL, incl, 31);
-    if (n == 0) continue;
-    if (lane == 0) atomicSub(&S->cnt[kind], n);
-    {
-      int o = incl - pc;
-      while (claimed) {
-        const int b = __ffs(claimed) - 1;
-        claimed &= claimed - 1;
-        S->batch[warp * LANES + o++] = (uint16_t)(lane * 32 + b);
+      const int nk = (int)(key & 31u);
+      if (lane == 0) {
+        const int old = atomicExch(&S->kind, nk);  // several warps may switch at once: account for the change once
+        if (old != nk) {
+          if (old >= 0) atomicSub(&GS->servers[old], 1);
+          atomicAdd(&GS->servers[nk], 1);
+        }
       }
+      kind = nk;
     }
-    __syncwarp();
-    const bool have = lane < n;
-    const unsigned idx = have ? S->batch[warp * LANES + lane] : 0u;
-    __threadfence_block();
-    CAAA_LAP(0);  // idle + select + claim
-    d_batches++;
-    d_items += (unsigned)n;
-    const unsigned mhave = __ballot_sync(FULL, have);
-    bool need_start = have && kind == Q_FREE;
-    bool live = have && kind != Q_FREE;
-    if (kind != Q_FREE) {  // ---- copy the games in: all 32 lanes move one game at a time (coalesced, asynchronous) ----
-      for (int j = 0; j < n; j++) {
-        const unsigned ij = __shfl_sync(FULL, idx, j);
-        const uint32_t* src = pool + (size_t)ij * GAME_WORDS;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + j);
+    bool have = false;   // this lane holds a game of phase `kind`
+    unsigned idx = 0;    // its pool entry
+    bool first = true;
+    for (;;) {  // ---- serve `kind`: (re)fill the free lanes, run, route the finished games, repeat while games yield ----
+      const unsigned mhave0 = __ballot_sync(FULL, have);
+      const unsigned free_lanes = ~mhave0 & LANE_MASK;
+      int n_new = free_lanes ? claim(kind, __popc(free_lanes)) : 0;
+      if (first && n_new == 0) break;
+      first = false;
+      CAAA_LAP(0);  // idle + select + claim
+      if (n_new > 0) {
+        d_batches++;
+        d_items += (unsigned)n_new;
+        __threadfence();
+        // the j-th new entry goes to the j-th free lane
+        const int my_rank = __popc(free_lanes & ((1u << lane) - 1u));
+        const bool got = ((free_lanes >> lane) & 1u) && my_rank < n_new;
+        if (got) {
+          idx = batch[my_rank];
+          have = true;
+          S->target[warp * LANES + my_rank] = (uint8_t)lane;
+        }
+        __syncwarp();
+        if (kind != Q_FREE) {  // copy the games in: all 32 lanes move one game at a time (coalesced), 4 games in flight
+          for (int j0 = 0; j0 < n_new; j0 += 4) {
+            uint32_t r[4][KW];
 #pragma unroll
-        for (int k = 0; k < (GAME_WORDS + 31) / 32; k++)
-          if (k * 32 + lane < GAME_WORDS) cp_async4(dst + k * 32 + lane, src + k * 32 + lane);
-      }
-      cp_async_wait_all();
-      __syncwarp();
-      CAAA_LAP(1);  // copy in
-      // ---- run the phase on all of them in lockstep ----
-      if (have) {
-        switch (kind) {
-          case CAAA_PH_MOVE_FIGHTERS: move_fighter_units<false>(g, cx, mhave); break;
-          case CAAA_PH_MOVE_BOMBERS: move_bomber_units<false>(g, cx, mhave); break;
-          case CAAA_PH_STAGE_TRANSPORTS: stage_transport_units<false>(g, cx, mhave); break;
-          case CAAA_PH_MOVE_TANKS: move_land_unit_type<false>(g, cx, mhave, TANKS, CAAA_PH_MOVE_TANKS); break;
-          case CAAA_PH_MOVE_ARTILLERY: move_land_unit_type<false>(g, cx, mhave, ARTILLERY, CAAA_PH_MOVE_ARTILLERY); break;
-          case CAAA_PH_MOVE_INFANTRY: move_land_unit_type<false>(g, cx, mhave, INFANTRY, CAAA_PH_MOVE_INFANTRY); break;
-          case CAAA_PH_MOVE_TRANSPORTS: move_transport_units<false>(g, cx, mhave); break;
-          case CAAA_PH_MOVE_SUBS: move_subs<false>(g, cx, mhave); break;
-          case CAAA_PH_MOVE_SHIPS: move_destroyers_battleships<false>(g, cx, mhave); break;
-          case CAAA_PH_SEA_BATTLES: resolve_sea_battles<false>(g, cx, mhave); break;
-          case CAAA_PH_UNLOAD_TRANSPORTS: unload_transports<false>(g, cx, mhave); break;
-          case CAAA_PH_LAND_BATTLES: resolve_land_battles<false>(g, cx, mhave); break;
-          case CAAA_PH_MOVE_AA_GUNS: move_land_unit_type<false>(g, cx, mhave, AA_GUNS, CAAA_PH_MOVE_AA_GUNS); break;
-          case CAAA_PH_LAND_FIGHTERS: land_fighter_units<false>(g, cx, mhave); break;
-          case CAAA_PH_LAND_BOMBERS: land_bomber_units<false>(g, cx, mhave); break;
-          default: {  // end of turn, reference src/engine.cpp:4229-4241
-            buy_units<false>(g, cx, mhave);
-            crash_air_units(g, cx);
-            reset_units_fully(g);
-            collect_money(g, cx);
-            rotate_turns(g, cx);
-            g->turns++;
-            const double score = evaluate_state(g, cx);
-            if (!(score > 0.01 && score < 0.99 && g->turns < 1000)) {
-              const unsigned long long gi = ((unsigned long long)g->game_hi << 32 | g->game_lo) - a.first_game_id;
-              finish_playout<STATS>(g, score, gi, a, tot);
-              live = false;
-              need_start = true;
+            for (int jj = 0; jj < 4; jj++) {
+              const unsigned ij = batch[(j0 + jj) < n_new ? (j0 + jj) : 0];
+              const uint32_t* src = pool + (size_t)ij * GAME_WORDS;
+#pragma unroll
+              for (int k = 0; k < KW; k++)
+                if (j0 + jj < n_new && k * 32 + lane < GAME_WORDS) r[jj][k] = __ldcg(src + k * 32 + lane);
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              const int t = S->target[warp * LANES + ((j0 + jj) < n_new ? (j0 + jj) : 0)];  // slot of the (j0+jj)-th new entry
+              uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + t);
+#pragma unroll
+              for (int k = 0; k < KW; k++)
+                if (j0 + jj < n_new && k * 32 + lane < GAME_WORDS) dst[k * 32 + lane] = r[jj][k];
             }
           }
+        }
+        __syncwarp();
+        CAAA_LAP(1);  // copy in
+      }
+      const unsigned mhave = __ballot_sync(FULL, have);
+      if (mhave == 0) break;
+      // ---- run the phase on all held games in lockstep; it may yield when a quarter of the lanes are done and
+      // replacements are waiting ----
+      const int waiting = __shfl_sync(FULL, lane < NQ ? vcnt[lane] : 0, kind);
+      const int yield = (a.yield_lanes > 0 && waiting >= a.yield_lanes) ? a.yield_lanes : 0;
+      int res = PH_DONE;
+      bool live = have, need_start = false;
+      if (have) {
+        switch (kind) {
+          case CAAA_PH_MOVE_FIGHTERS: res = move_fighter_units<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_MOVE_BOMBERS: res = move_bomber_units<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_STAGE_TRANSPORTS: res = stage_transport_units<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_MOVE_TANKS: res = move_land_unit_type<false>(g, cx, mhave, TANKS, CAAA_PH_MOVE_TANKS, yield); break;
+          case CAAA_PH_MOVE_ARTILLERY: res = move_land_unit_type<false>(g, cx, mhave, ARTILLERY, CAAA_PH_MOVE_ARTILLERY, yield); break;
+          case CAAA_PH_MOVE_INFANTRY: res = move_land_unit_type<false>(g, cx, mhave, INFANTRY, CAAA_PH_MOVE_INFANTRY, yield); break;
+          case CAAA_PH_MOVE_TRANSPORTS: res = move_transport_units<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_MOVE_SUBS: res = move_subs<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_MOVE_SHIPS: res = move_destroyers_battleships<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_SEA_BATTLES: res = resolve_sea_battles<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_UNLOAD_TRANSPORTS: res = unload_transports<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_LAND_BATTLES: res = resolve_land_battles<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_MOVE_AA_GUNS: res = move_land_unit_type<false>(g, cx, mhave, AA_GUNS, CAAA_PH_MOVE_AA_GUNS, yield); break;
+          case CAAA_PH_LAND_FIGHTERS: res = land_fighter_units<false>(g, cx, mhave, yield); break;
+          case CAAA_PH_LAND_BOMBERS: res = land_bomber_units<false>(g, cx, mhave, yield); break;
+          case Q_EOT: {  // reference src/engine.cpp:4229-4241
+            res = buy_units<false>(g, cx, mhave, yield);
+            if (res != PH_YIELDED) {
+              crash_air_units(g, cx);
+              reset_units_fully(g);
+              collect_money(g, cx);
+              rotate_turns(g, cx);
+              g->turns++;
+              const double score = evaluate_state(g, cx);
+              if (!(score > 0.01 && score < 0.99 && g->turns < 1000)) {
+                const unsigned long long gi = ((unsigned long long)g->game_hi << 32 | g->game_lo) - a.first_game_id;
+                finish_playout<STATS>(g, score, gi, a, tot);
+                live = false;
+                need_start = true;
+              }
+            }
+            break;
+          }
+          default:  // Q_FREE: an empty pool entry
+            live = false;
+            need_start = true;
+            break;
         }
       }
       __syncwarp();
       CAAA_LAP(2);  // compute
-    }
-    // ---- (re)start pool entries from the ticket counter: one fetch per warp, cooperative copy of the start state ----
-    bool retired = false;
-    for (;;) {
-      const unsigned need = __ballot_sync(FULL, need_start);
-      if (need == 0) break;
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(a.ticket, (unsigned long long)__popc(need));
-      base = __shfl_sync(FULL, base, 0);
-      unsigned m = need;
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        const unsigned long long gj = base + (unsigned)__popc(need & ((1u << j) - 1u));
-        if (gj < a.n_games) {
-          const unsigned long long sj = one_state ? 0ULL : gj / a.rollouts_per_state;
-          const uint32_t* src = a.templates + sj * GAME_WORDS;
-          uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + j);
+      // ---- (re)start pool entries from the ticket counter: one fetch per warp, cooperative copy of the start state ----
+      bool retired = false;
+      for (;;) {
+        const unsigned need = __ballot_sync(FULL, need_start);
+        if (need == 0) break;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(a.ticket, (unsigned long long)__popc(need));
+        base = __shfl_sync(FULL, base, 0);
+        unsigned m = need;
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const unsigned long long gj = base + (unsigned)__popc(need & ((1u << j) - 1u));
+          if (gj < a.n_games) {
+            const unsigned long long sj = one_state ? 0ULL : gj / a.rollouts_per_state;
+            const uint32_t* src = a.templates + sj * GAME_WORDS;
+            uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + j);
 #pragma unroll
-          for (int k = 0; k < (GAME_WORDS + 31) / 32; k++)
-            if (k * 32 + lane < GAME_WORDS) cp_async4(dst + k * 32 + lane, src + k * 32 + lane);
-        }
-      }
-      cp_async_wait_all();
-      __syncwarp();
-      if (need_start) {
-        const unsigned long long gi = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-        if (gi < a.n_games) {
-          const unsigned long long id = a.first_game_id + gi;
-          g->game_lo = (uint32_t)id;
-          g->game_hi = (uint32_t)(id >> 32);
-          const double score = a.scores0[one_state ? 0ULL : gi / a.rollouts_per_state];
-          if (score > 0.01 && score < 0.99) {
-            live = true;
-            need_start = false;
-          } else {
-            finish_playout<STATS>(g, score, gi, a, tot);  // already terminal: zero turns, take another ticket
+            for (int k = 0; k < KW; k++)
+              if (k * 32 + lane < GAME_WORDS) cp_async4(dst + k * 32 + lane, src + k * 32 + lane);
           }
-        } else {
-          need_start = false;
-          retired = true;
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (need_start) {
+          const unsigned long long gi = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+          if (gi < a.n_games) {
+            const unsigned long long id = a.first_game_id + gi;
+            g->game_lo = (uint32_t)id;
+            g->game_hi = (uint32_t)(id >> 32);
+            const double score = a.scores0[one_state ? 0ULL : gi / a.rollouts_per_state];
+            if (score > 0.01 && score < 0.99) {
+              live = true;
+              need_start = false;
+            } else {
+              finish_playout<STATS>(g, score, gi, a, tot);  // already terminal: zero turns, take another ticket
+            }
+          } else {
+            need_start = false;
+            retired = true;
+          }
         }
       }
-    }
-    CAAA_LAP(3);  // restart
-    // ---- route every live game to the next phase that has work for it and copy it back out ----
-    int nxt = -1;
-    if (live) {
-      uint32_t w = g->work & W_ALL_MOVES;
-      if (kind < Q_EOT) w &= ~((2u << kind) - 1u);
-      nxt = w ? __ffs(w) - 1 : Q_EOT;
-    }
-    __syncwarp();
-    for (int j = 0; j < n; j++) {
-      if (__shfl_sync(FULL, nxt, j) < 0) continue;
-      const unsigned ij = __shfl_sync(FULL, idx, j);
-      uint32_t* dst = pool + (size_t)ij * GAME_WORDS;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(warp_games + j);
+      CAAA_LAP(3);  // restart
+      // ---- route every finished game to the next phase that has work for it and copy it back out; games that
+      // yielded stay in their slots ----
+      int nxt = -1;
+      if (have && live && res != PH_YIELDED) {
+        uint32_t w = g->work & W_ALL_MOVES;
+        if (kind < Q_EOT) w &= ~((2u << kind) - 1u);  // after the end of a turn (or a fresh start) every phase is open again
+        nxt = w ? __ffs(w) - 1 : Q_EOT;
+      }
+      unsigned mout = __ballot_sync(FULL, nxt >= 0);
+      __syncwarp();
+      while (mout) {
+        const int j = __ffs(mout) - 1;
+        mout &= mout - 1;
+        const unsigned ij = __shfl_sync(FULL, idx, j);
+        uint32_t* dst = pool + (size_t)ij * GAME_WORDS;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(warp_games + j);
 #pragma unroll
-      for (int k = 0; k < (GAME_WORDS + 31) / 32; k++)
-        if (k * 32 + lane < GAME_WORDS) dst[k * 32 + lane] = src[k * 32 + lane];
+        for (int k = 0; k < KW; k++)
+          if (k * 32 + lane < GAME_WORDS) __stcg(dst + k * 32 + lane, src[k * 32 + lane]);
+      }
+      __threadfence();
+      __syncwarp();
+      {
+        const unsigned peers = __match_any_sync(FULL, nxt);
+        if (nxt >= 0) {
+          atomicOr(&GS->bm[nxt][idx >> 5], 1u << (idx & 31u));
+          if (lane == __ffs(peers) - 1) atomicAdd(&GS->cnt[nxt], __popc(peers));
+        }
+      }
+      const unsigned nret = __popc(__ballot_sync(FULL, retired));
+      if (lane == 0 && nret) atomicAdd(&GS->retired, (int)nret);
+      if (have && res != PH_YIELDED) have = false;  // routed on, retired or finished: the lane is free again
+      CAAA_LAP(4);  // copy out + publish
+      if (!__any_sync(FULL, have)) break;  // nobody yielded: pick the next phase
     }
-    __threadfence_block();
-    __syncwarp();
-    if (nxt >= 0) {
-      atomicOr(&S->bm[nxt][idx >> 5], 1u << (idx & 31u));
-      atomicAdd(&S->cnt[nxt], 1);
-    }
-    const unsigned nret = __popc(__ballot_sync(FULL, retired));
-    if (lane == 0 && nret) atomicAdd(&S->retired, (int)nret);
-    CAAA_LAP(4);  // copy out + publish
   }
 #undef CAAA_LAP
   if (dbg != nullptr && lane == 0) {

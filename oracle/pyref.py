@@ -243,6 +243,14 @@ class HostSim(_Engine):
     def stuck(self):
         return bool(self.lib.caaa_hostsim_stuck())
 
+    def rollout_many_sliced(self, state, first_game_id, n, budget):
+        """Playouts in which every phase yields after `budget` loop iterations and resumes from its saved cursor."""
+        st = np.zeros(n, dtype=STATS_DTYPE)
+        buf = np.ascontiguousarray(state).view(np.uint8).reshape(-1)
+        self.lib.caaa_hostsim_rollout_many_sliced(buf.ctypes.data_as(C.c_void_p), C.c_int64(first_game_id), C.c_int(n), C.c_int(budget),
+                                                  st.ctypes.data_as(C.c_void_p))
+        return st
+
 
 def have_ref():
     return os.path.exists(Ref.PATH)

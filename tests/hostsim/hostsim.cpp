@@ -154,7 +154,25 @@ extern "C" uint8_t caaa_hostsim_stream_byte(uint64_t seed, uint64_t game_id, uin
   for (uint32_t d = g.draws; d <= draw_index; d++) b = next_byte(&g, cx);
   return b;
 }
-// playout driven without the phases >= BUY being special: kept for API compatibility with the tests
+// playout in which every phase yields after `budget` loop iterations and is resumed from its saved cursor until it
+// is done -- the way the phase-regrouped kernel time-slices long phases
+extern "C" void caaa_hostsim_rollout_many_sliced(const void* s, int64_t first, int n, int budget, CaaaRolloutStats* st) {
+  for (int i = 0; i < n; i++) {
+    Game* g = &g_game;
+    import_state(g, (const uint8_t*)s);
+    begin_playout(g, g_cx, (uint64_t)first + (uint64_t)i);
+    double score = evaluate_state(g, g_cx);
+    while (score > 0.01 && score < 0.99 && g->turns < 1000) {
+      for (int ph = 0; ph < CAAA_PH_COUNT; ph++)
+        while (run_phase<false>(g, g_cx, ph, 0xffffffffu, budget) == PH_YIELDED) {
+        }
+      g->turns++;
+      score = evaluate_state(g, g_cx);
+    }
+    if (g->player % 2 == 1) score = 1 - score;
+    fill_stats(g, score, st + i);
+  }
+}
 extern "C" void caaa_hostsim_rollout_many_routed(const void* s, int64_t first, int n, CaaaRolloutStats* st) {
-  for (int i = 0; i < n; i++) play(s, (uint64_t)first + (uint64_t)i, st + i);
+  caaa_hostsim_rollout_many_sliced(s, first, n, 1, st);
 }

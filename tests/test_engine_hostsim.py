@@ -90,3 +90,17 @@ def test_expansion_mode_bit_exact(port, hostsim):
             if stuck_p:
                 break  # the reference never returns from this action; both implementations flag it
             assert np.array_equal(sp, sh), (walk, step)
+
+
+def test_phases_resume_from_their_saved_cursor(port, hostsim):
+    """The phase-regrouped kernel time-slices long phases: a phase yields, its loop cursor is saved in the game and
+    it is resumed later.  Slicing (here: after every 1, 2 or 5 loop iterations) must not change a single byte."""
+    s = pyref.start_state()
+    port.set_stream(1, SEED)
+    hostsim.set_stream(1, SEED)
+    want = port.rollout_many(s, 0, 400)
+    for budget in (1, 2, 5):
+        assert np.array_equal(want, hostsim.rollout_many_sliced(s, 0, 400, budget)), budget
+    snaps = snapshots(port, 12)
+    for i, st in enumerate(snaps[::3]):
+        assert np.array_equal(port.rollout_many(st, 5000 + 10 * i, 2), hostsim.rollout_many_sliced(st, 5000 + 10 * i, 2, 1)), i
