@@ -381,8 +381,8 @@ struct Context {
   bool sync_phases = false;  // CAAA_SYNC=1: CTA barrier after every phase (A/B knob)
   bool streaming = true;     // CAAA_ROLLOUT_KERNEL=lockstep selects the walk-the-pipeline kernel instead
   int pool_mult = 3;         // pool entries per shared-memory slot (CAAA_POOL_MULT)
-  int lanes = 32;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
-  int group_size = 8;        // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
+  int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
+  int group_size = 16;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
   void* d_pool = nullptr;    // per-SM game pools of the phase-regrouped kernel
   size_t pool_cap = 0;
 };
@@ -475,9 +475,9 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     else                                                                                                                            \
       rollout_kernel_stream<false, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
   } while (0)
-    if (c.lanes == 16) CAAA_LAUNCH_STREAM(16);
+    if (c.lanes == 32) CAAA_LAUNCH_STREAM(32);
     else if (c.lanes == 8) CAAA_LAUNCH_STREAM(8);
-    else CAAA_LAUNCH_STREAM(32);
+    else CAAA_LAUNCH_STREAM(16);
     if (d_dbg != nullptr) {
       StreamDbg h;
       cudaStreamSynchronize(stream);
@@ -537,10 +537,10 @@ int caaa_gpu_init(int device) {
   if (c.pool_mult < 1) c.pool_mult = 1;
   if (c.pool_mult > MAX_POOL_MULT) c.pool_mult = MAX_POOL_MULT;
   const char* ln = std::getenv("CAAA_LANES");
-  c.lanes = ln ? std::atoi(ln) : 32;
-  if (c.lanes != 8 && c.lanes != 16) c.lanes = 32;
+  c.lanes = ln ? std::atoi(ln) : 16;
+  if (c.lanes != 8 && c.lanes != 32) c.lanes = 16;
   const char* gs = std::getenv("CAAA_GROUP");
-  c.group_size = gs ? std::atoi(gs) : 8;
+  c.group_size = gs ? std::atoi(gs) : 16;
   if (c.group_size < 1) c.group_size = 1;
   if (c.group_size > MAX_GROUP) c.group_size = MAX_GROUP;
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));

@@ -28,11 +28,19 @@ namespace e2 {
 CAAA_HD constexpr uint32_t W(int ph) { return 1u << ph; }
 constexpr uint32_t W_ALL_MOVES = 0x7fffu;  // phases 0..14
 
-CAAA_HD_NOINLINE uint8_t next_byte(Game* g, const RunCtx cx) {
+CAAA_HD_NOINLINE void refill_rng(Game* g, const RunCtx cx, uint32_t d) {
+  philox4x32_10(d >> 4, g->game_lo, g->game_hi, 0u, cx.seed_lo, cx.seed_hi, g->rng);
+}
+CAAA_HD uint32_t next_byte(Game* g, const RunCtx cx) {
   const uint32_t d = g->draws++;
   const uint32_t k = d & 15u;
-  if (k == 0) philox4x32_10(d >> 4, g->game_lo, g->game_hi, 0u, cx.seed_lo, cx.seed_hi, g->rng);
-  return (uint8_t)(g->rng[k >> 2] >> (8u * (k & 3u)));
+  if (k == 0) refill_rng(g, cx, d);  // one Philox block serves 16 draws
+  return (g->rng[k >> 2] >> (8u * (k & 3u))) & 0xffu;
+}
+// byte % n for n in 1..31 without a division: q = byte * ceil(2^16 / n) >> 16 is exact for byte < 256
+CAAA_HD uint32_t mod_small(const RunCtx cx, uint32_t byte, uint32_t n) {
+  const uint32_t q = (byte * CAAA_TAB(cx)->recip16[n & 31u]) >> 16;
+  return byte - q * n;
 }
 
 // ---- cache refresh, engine.cpp:642-814 ----
@@ -157,7 +165,9 @@ template <bool EXPAND>
 CAAA_HD uint8_t ai_input(Game* g, const RunCtx cx) {  // getAIInput 1291-1297
   g->answers_remaining--;
   if (EXPAND && g->use_selected) return g->selected_action;
-  return g->vm[next_byte(g, cx) % g->nvm];
+  const uint32_t n = g->nvm;
+  const uint32_t b = next_byte(g, cx);
+  return g->vm[n < 32u ? mod_small(cx, b, n) : b % n];
 }
 CAAA_HD bool unlucky_team(const Game* g, const RunCtx cx) { return CAAA_TAB(cx)->t.is_allied[g->cur][g->unlucky % NP] != 0; }
 CAAA_HD uint32_t attacker_hits(Game* g, const RunCtx cx, int dmg) {  // 2552-2565
@@ -673,8 +683,8 @@ CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min,
     int src = 0, moves = 0;
 #pragma unroll 1
     for (; cell < NL * mm; cell++) {
-      src = cell / mm;
-      moves = mm - cell % mm;
+      src = cell >> (mm - 1);  // mm is 1 or 2
+      moves = mm - (cell & (mm - 1));
       arr = lu_ptr(g, src, ut);
       if (arr[moves] != 0) break;
       fresh = true;

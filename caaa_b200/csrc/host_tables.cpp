@@ -156,6 +156,7 @@ void build_tables(CaaaTables* out) {
 void build_dev_tables(DevTables* out) {
   std::memset(out, 0, sizeof(*out));
   build_tables(&out->t);
+  for (uint32_t n = 1; n < 32; n++) out->recip16[n] = 65536u / n + 1u;
   for (int pi = 0; pi < NP; pi++) {  // refresh_allies (engine.cpp:716-725) for every player to move
     for (int p = 0; p < NP; p++) {
       if (out->t.is_allied[pi][(pi + p) % NP]) out->allied_mask[pi] |= (uint8_t)(1u << p);

@@ -99,6 +99,7 @@ struct DevTables {
   uint8_t allied_abs[NP];     // bit a set <=> absolute player a is allied with the player to move
   uint8_t enemies_abs[NP][4]; // absolute ids of the enemies, in the relative order above
   uint8_t pad2_[3];
+  uint32_t recip16[32];       // ceil(2^16 / n): byte % n without a division (n = 0 is never used)
 };
 
 // status bits reported per game (0 = clean)

@@ -235,7 +235,11 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       // ---- run the phase on all held games in lockstep; it may yield when a quarter of the lanes are done and
       // replacements are waiting ----
       const int waiting = __shfl_sync(FULL, lane < NQ ? vcnt[lane] : 0, kind);
-      const int yield = (a.yield_lanes > 0 && waiting >= a.yield_lanes) ? a.yield_lanes : 0;
+      // a_yield_pct > 0: the phase yields once that share of the batch is done; the stragglers are queued for the same
+      // phase again (cursor saved in the game) and meet other stragglers there
+      const int nh = __popc(mhave);
+      const int yield = (a.yield_lanes > 0 && nh >= 8) ? (nh * a.yield_lanes + 99) / 100 : 0;
+      (void)waiting;
       int res = PH_DONE;
       bool live = have, need_start = false;
       if (have) {
@@ -328,7 +332,9 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       // ---- route every finished game to the next phase that has work for it and copy it back out; games that
       // yielded stay in their slots ----
       int nxt = -1;
-      if (have && live && res != PH_YIELDED) {
+      if (have && live && res == PH_YIELDED) {
+        nxt = kind;
+      } else if (have && live) {
         uint32_t w = g->work & W_ALL_MOVES;
         if (kind < Q_EOT) w &= ~((2u << kind) - 1u);  // after the end of a turn (or a fresh start) every phase is open again
         nxt = w ? __ffs(w) - 1 : Q_EOT;
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       }
       const unsigned nret = __popc(__ballot_sync(FULL, retired));
       if (lane == 0 && nret) atomicAdd(&GS->retired, (int)nret);
-      if (have && res != PH_YIELDED) have = false;  // routed on, retired or finished: the lane is free again
+      have = false;  // routed on, requeued, retired or finished: every lane is free again
       CAAA_LAP(4);  // copy out + publish
       if (!__any_sync(FULL, have)) break;  // nobody yielded: pick the next phase
     }
