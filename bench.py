@@ -10,8 +10,8 @@ is sharded by game-id range with no data-path collective (weak scaling).  Rank 0
   value     playouts/s, states and results resident in HBM (device-pointer C-ABI entry point)
   e2e       same metric through the host-buffer C-ABI call (H2D of the states, D2H of the results inside)
   roofline  HBM roofline of the rollout kernel from algorithmic bytes (1340 B per ply)
-            and the live CUDA-event duration; the binding limit of this kernel is instruction issue,
-            which is reported from ncu under profiles/
+            and the live CUDA-event duration; the binding limit of this kernel is per-warp latency /
+            instruction issue, which is reported from ncu under profiles/
   cpu_baseline  the reference's own CPU rollout loop (oracle/_ref) on ONE host core, bounded sample
 
 `--impl reference` times the reference's CPU loop on all host cores instead (one process per core: the
@@ -33,6 +33,13 @@ sys.path.insert(0, ROOT)
 SEED = 0xCAAA2024
 BYTES_PER_PLY = 1340  # one 670-byte GameState read + written per player-turn
 METRIC = "playouts/sec"
+# kernels of one rollout batch: prepare_kernel (import of the start states), group_init_kernel (phase bitmaps),
+# rollout_kernel_stream (the playouts)
+KERNELS_PER_BATCH = 3
+ROLLOUT_KERNEL = "rollout_kernel_stream<false, 16>"
+# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_kernel_stream launch of 2**20 playouts
+# (profiles/r1_ncu_summary.md); None when this run uses another batch size
+NCU_DRAM_BYTES_PER_1M_LAUNCH = None
 
 
 def measured_peaks():
@@ -201,7 +208,7 @@ def ours(args):
         barrier()
         ev[k][0].record()
         device_step(args.warmup + k)
-        launches += 1
+        launches += KERNELS_PER_BATCH
         ev[k][1].record()
     barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
@@ -254,11 +261,13 @@ def ours(args):
                                    "(game_data.json), bit-exact vs the patched reference",
                        "playouts_per_gpu_per_step": P, "seed": SEED, "plies_per_sec": plies_total / total_s,
                        "plies_per_playout": plies_total / (world * P * args.steps), "flagged_playouts": float(flagged.item()),
-                       "l2": "256 MiB write between timed steps (untimed); kernel working set lives in shared memory",
+                       "l2": "256 MiB write between timed steps (untimed); the game pool (~100 MB) is rewritten by every step",
                        "sharding": "game-id ranges per rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "rollout_kernel<false>",
-                         "note": "algorithmic 1340 B/ply; the kernel is issue/latency bound, see profiles/"},
+                         "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if P == (1 << 20) else None, "peak_source": peak_src,
+                         "kernel": ROLLOUT_KERNEL,
+                         "note": "algorithmic 1340 B/ply; the kernel is bound by per-warp latency and lane occupancy, "
+                                 "not by HBM: see profiles/r1_ncu_summary.md"},
             "e2e": {"value": e2e_value, "unit": "playouts/s", "h2d_bytes_per_step": 670, "d2h_bytes_per_step": 8 * P + 56},
             "gpu_launches": launches, "clocks": clocks,
         }

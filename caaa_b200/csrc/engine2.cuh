@@ -361,7 +361,9 @@ CAAA_HD_NOINLINE int move_fighter_units(Game* g, const RunCtx cx, unsigned min, 
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -371,6 +373,7 @@ CAAA_HD_NOINLINE int move_fighter_units(Game* g, const RunCtx cx, unsigned min, 
       if (arr[4] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (src >= NA) {
       active = false;
       continue;
@@ -497,7 +500,9 @@ CAAA_HD_NOINLINE int move_bomber_units(Game* g, const RunCtx cx, unsigned min, i
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -507,6 +512,7 @@ CAAA_HD_NOINLINE int move_bomber_units(Game* g, const RunCtx cx, unsigned min, i
       if (arr[6] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (src >= NL) {
       active = false;
       continue;
@@ -586,7 +592,9 @@ CAAA_HD_NOINLINE int stage_transport_units(Game* g, const RunCtx cx, unsigned mi
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -600,6 +608,7 @@ CAAA_HD_NOINLINE int stage_transport_units(Game* g, const RunCtx cx, unsigned mi
       if (arr[staging] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (cell >= 4 * NS) {
       active = false;
       continue;
@@ -676,7 +685,9 @@ CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min,
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -689,6 +700,7 @@ CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min,
       if (arr[moves] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (cell >= NL * mm) {
       active = false;
       continue;
@@ -778,7 +790,9 @@ CAAA_HD_NOINLINE int move_transport_units(Game* g, const RunCtx cx, unsigned min
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -792,6 +806,7 @@ CAAA_HD_NOINLINE int move_transport_units(Game* g, const RunCtx cx, unsigned min
       if (arr[cs] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (cell >= 6 * NS * 2) {
       active = false;
       continue;
@@ -862,7 +877,9 @@ CAAA_HD_NOINLINE int move_subs(Game* g, const RunCtx cx, unsigned min, int yield
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -872,6 +889,7 @@ CAAA_HD_NOINLINE int move_subs(Game* g, const RunCtx cx, unsigned min, int yield
       if (arr[2] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (s >= NS) {
       active = false;
       continue;
@@ -950,7 +968,9 @@ CAAA_HD_NOINLINE int move_destroyers_battleships(Game* g, const RunCtx cx, unsig
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -964,6 +984,7 @@ CAAA_HD_NOINLINE int move_destroyers_battleships(Game* g, const RunCtx cx, unsig
       if (arr[unmoved] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (cell >= 5 * NS) {
       active = false;
       continue;
@@ -1204,7 +1225,9 @@ CAAA_HD_NOINLINE int resolve_sea_battles(Game* g, const RunCtx cx, unsigned min,
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     if (!in_battle) {  // next flagged sea with own units (one sea per iteration keeps the lanes together)
@@ -1376,7 +1399,9 @@ CAAA_HD_NOINLINE int unload_transports(Game* g, const RunCtx cx, unsigned min, i
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -1389,6 +1414,7 @@ CAAA_HD_NOINLINE int unload_transports(Game* g, const RunCtx cx, unsigned min, i
       if (arr[1] != 0) break;  // STATES_UNLOADING is 1 for every loaded transport type
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (cell >= 6 * NS) {
       active = false;
       continue;
@@ -1485,7 +1511,9 @@ CAAA_HD_NOINLINE int resolve_land_battles(Game* g, const RunCtx cx, unsigned min
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     if (!in_battle) {
@@ -1666,7 +1694,9 @@ CAAA_HD_NOINLINE int land_fighter_units(Game* g, const RunCtx cx, unsigned min, 
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -1679,6 +1709,7 @@ CAAA_HD_NOINLINE int land_fighter_units(Game* g, const RunCtx cx, unsigned min, 
       if (arr[cs] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (cell >= 3 * NA) {
       active = false;
       continue;
@@ -1756,7 +1787,9 @@ CAAA_HD_NOINLINE int land_bomber_units(Game* g, const RunCtx cx, unsigned min, i
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     uint8_t* arr = nullptr;
@@ -1769,6 +1802,7 @@ CAAA_HD_NOINLINE int land_bomber_units(Game* g, const RunCtx cx, unsigned min, i
       if (arr[cs] != 0) break;
       fresh = true;
     }
+    converge<!EXPAND>(mact);
     if (cell >= 5 * NA) {
       active = false;
       continue;
@@ -1849,7 +1883,9 @@ CAAA_HD_NOINLINE int buy_units(Game* g, const RunCtx cx, unsigned min, int yield
   }
   bool active = true, stop = false;
   int steps = 0;
-  while (vote_any<!EXPAND>(m, active)) {
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
     if (f >= g->nfact[cur]) {

@@ -128,6 +128,16 @@ CAAA_HD bool should_yield(unsigned m, bool active, int yield, int& steps) {
   return steps++ >= yield;
 }
 
+// Re-joins the lanes of `mask` (the lanes that entered this loop iteration) after a loop in which they ran
+// different trip counts; the compiler does not place a reconvergence point there by itself.
+template <bool V>
+CAAA_HD void converge(unsigned mask) {
+#if defined(__CUDA_ARCH__)
+  if (V) __syncwarp(mask);
+#endif
+  (void)mask;
+}
+
 // ---- accessors ----
 CAAA_HD constexpr uint32_t off_lu(int t) { return off_land(t) - 4u; }
 CAAA_HD uint8_t* lu_ptr(Game* g, int l, int t) { return g->lu[l] + off_lu(t); }
