@@ -53,7 +53,8 @@ struct RolloutArgs {
   CaaaBatchSummary* summary;  // optional
   unsigned long long* ticket;
   int switch_below;
-  int yield_lanes;   // a phase yields when this many of its lanes are done and as many replacements wait (0 = never)
+  int yield_lanes;   // a phase yields once this percentage of its batch is done; stragglers are requeued (0 = never)
+  int scan_rounds;   // bitmap words / 32 a claim may look at
 };
 
 // Import every start / leaf state once: reference layout -> Game with all derived caches, ready to be
@@ -452,6 +453,9 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     a.switch_below = sb ? std::atoi(sb) : 16;
     const char* yl = std::getenv("CAAA_YIELD");
     a.yield_lanes = yl ? std::atoi(yl) : 0;
+    const char* sr = std::getenv("CAAA_SCAN_ROUNDS");
+    a.scan_rounds = sr ? std::atoi(sr) : 4;
+    if (a.scan_rounds < 1) a.scan_rounds = 1;
   }
   const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
   const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);

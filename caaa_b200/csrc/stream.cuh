@@ -72,6 +72,10 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long ld_vol_u64(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
 struct StreamDbg {
   unsigned long long batches, items, t[6];
 };
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   volatile int* vsrv = GS->servers;
   volatile int* vkind = &S->kind;
   volatile int* vretired = &GS->retired;
-  unsigned scan_rot = (unsigned)(blockIdx.x * 7 + warp * 3);  // where this warp starts scanning the bitmaps
+  unsigned scan_rot = (unsigned)((blockIdx.x * 7 + warp * 3) * 32) % (unsigned)(((bm_words + 31) / 32) * 32);  // where this warp starts scanning
   const int switch_below = a.switch_below;  // leave a phase when fewer entries than this wait for it
   constexpr unsigned LANE_MASK = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
   constexpr int KW = (GAME_WORDS + 31) / 32;
@@ -124,8 +128,12 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   auto claim = [&](int kind, int want) -> int {
     int n = 0;
     const int rounds = (bm_words + 31) / 32;
-    for (int r = 0; r < rounds && n < want; r++) {
-      const int wi = (int)((scan_rot + (unsigned)(r * 32 + lane)) % (unsigned)(rounds * 32));
+    // a claim looks at no more than `scan_rounds` x 32 words, starting where the previous one stopped: entries it
+    // misses are found by a later claim, and a nearly empty phase does not cost a scan of the whole bitmap
+    const int look = rounds < a.scan_rounds ? rounds : a.scan_rounds;
+    for (int r = 0; r < look && n < want; r++) {
+      int wi = (int)scan_rot + r * 32 + lane;  // scan_rot < rounds * 32
+      if (wi >= rounds * 32) wi -= rounds * 32;
       uint32_t word = wi < bm_words ? *reinterpret_cast<volatile uint32_t*>(&GS->bm[kind][wi]) : 0u;
       if (!__any_sync(FULL, word != 0)) continue;
       int pc = __popc(word), incl = pc;
@@ -153,7 +161,8 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       }
       n += __shfl_sync(FULL, incl, 31);
     }
-    scan_rot += 32;
+    scan_rot += 32u * (unsigned)look;
+    while (scan_rot >= (unsigned)(rounds * 32)) scan_rot -= (unsigned)(rounds * 32);
     if (n > 0 && lane == 0) atomicSub(&GS->cnt[kind], n);
     __syncwarp();
     return n;
@@ -186,10 +195,11 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
     bool have = false;   // this lane holds a game of phase `kind`
     unsigned idx = 0;    // its pool entry
     bool first = true;
-    for (;;) {  // ---- serve `kind`: (re)fill the free lanes, run, route the finished games, repeat while games yield ----
+    const bool chaining = false;
+    for (;;) {  // ---- serve `kind`: fill the free lanes, run, route the finished games ----
       const unsigned mhave0 = __ballot_sync(FULL, have);
       const unsigned free_lanes = ~mhave0 & LANE_MASK;
-      int n_new = free_lanes ? claim(kind, __popc(free_lanes)) : 0;
+      int n_new = (free_lanes && !chaining) ? claim(kind, __popc(free_lanes)) : 0;
       if (first && n_new == 0) break;
       first = false;
       CAAA_LAP(0);  // idle + select + claim
@@ -230,7 +240,8 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         __syncwarp();
         CAAA_LAP(1);  // copy in
       }
-      const unsigned mhave = __ballot_sync(FULL, have);
+      const bool runs = have;
+      const unsigned mhave = __ballot_sync(FULL, runs);
       if (mhave == 0) break;
       // ---- run the phase on all held games in lockstep; it may yield when a quarter of the lanes are done and
       // replacements are waiting ----
@@ -241,8 +252,8 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       const int yield = (a.yield_lanes > 0 && nh >= 8) ? (nh * a.yield_lanes + 99) / 100 : 0;
       (void)waiting;
       int res = PH_DONE;
-      bool live = have, need_start = false;
-      if (have) {
+      bool live = runs, need_start = false;
+      if (runs) {
         switch (kind) {
           case CAAA_PH_MOVE_FIGHTERS: res = move_fighter_units<false>(g, cx, mhave, yield); break;
           case CAAA_PH_MOVE_BOMBERS: res = move_bomber_units<false>(g, cx, mhave, yield); break;
@@ -332,14 +343,15 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       // ---- route every finished game to the next phase that has work for it and copy it back out; games that
       // yielded stay in their slots ----
       int nxt = -1;
-      if (have && live && res == PH_YIELDED) {
+      if (runs && live && res == PH_YIELDED) {
         nxt = kind;
-      } else if (have && live) {
+      } else if (runs && live) {
         uint32_t w = g->work & W_ALL_MOVES;
         if (kind < Q_EOT) w &= ~((2u << kind) - 1u);  // after the end of a turn (or a fresh start) every phase is open again
         nxt = w ? __ffs(w) - 1 : Q_EOT;
       }
-      unsigned mout = __ballot_sync(FULL, nxt >= 0);
+      const bool keep = false;  // (a warp never holds on to a game: every phase is a hop through the pool)
+      unsigned mout = __ballot_sync(FULL, nxt >= 0 && !keep);
       __syncwarp();
       while (mout) {
         const int j = __ffs(mout) - 1;
@@ -354,6 +366,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       __threadfence();
       __syncwarp();
       {
+        if (keep) nxt = -1;
         const unsigned peers = __match_any_sync(FULL, nxt);
         if (nxt >= 0) {
           atomicOr(&GS->bm[nxt][idx >> 5], 1u << (idx & 31u));
@@ -364,7 +377,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       if (lane == 0 && nret) atomicAdd(&GS->retired, (int)nret);
       have = false;  // routed on, requeued, retired or finished: every lane is free again
       CAAA_LAP(4);  // copy out + publish
-      if (!__any_sync(FULL, have)) break;  // nobody yielded: pick the next phase
+      break;
     }
   }
 #undef CAAA_LAP
