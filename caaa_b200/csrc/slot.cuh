@@ -1,11 +1,5 @@
-// slot.cuh -- per-game working set ("slot") and the read-only tables, as they live in shared
-// memory while a CTA steps its games.
-//
-// One slot = the reference's 670-byte GameState (verbatim layout, include/caaa_types.h, reference
-// include/game_state.h:20-68) followed by the derived caches that the reference keeps in
-// file-scope globals (reference src/engine.cpp:120-159) and the per-game stream state.
-// The slot stride is an odd number of 32-bit words, so when the 32 lanes of a warp touch the
-// same field of 32 different games the accesses fall into 32 different banks.
+// slot.cuh -- unit-type tables as immediates and the read-only topology tables, as they live in shared
+// memory while a CTA steps its games.  The per-game working set itself is `Game` in game.cuh.
 #pragma once
 #include <stdint.h>
 #include "../../include/caaa_types.h"
@@ -109,36 +103,6 @@ enum : uint32_t {
 };
 constexpr int SEA_ROUND_CAP = 10000;
 
-struct GameSlot {
-  CaaaGameState st;   // 0..669: verbatim reference layout
-  uint8_t nvm;        // valid_moves_count
-  uint8_t canal_state;
-  // 672
-  int32_t tot_land[6][NL];  // total_player_land_units (row 5 = rotate_turns scratch)
-  int32_t tot_sea[6][NS];   // total_player_sea_units
-  int32_t enemy_count[NA];  // enemy_units_count
-  int32_t income[6];        // income_per_turn
-  int32_t large_cargo[NS];  // transports_with_large_cargo_space
-  int32_t small_cargo[NS];
-  int32_t carriers[NS];     // allied_carriers
-  int32_t answers_remaining;
-  uint32_t draws;           // random bytes consumed so far (= Philox draw index)
-  uint32_t rng[4];          // current 16-byte Philox block
-  uint32_t game_lo, game_hi;
-  int32_t turns;
-  uint32_t status;
-  int8_t nfact[6];          // total_factory_count
-  uint8_t factloc[6][NL];   // factory_locations
-  uint8_t cur_land[NL][NLT];  // current_player_land_unit_types
-  uint8_t cur_sea[NS][NST];   // current_player_sea_unit_types
-  uint8_t blockade[NS], edestroyers[NS];
-  uint8_t land_blocked[25], sea_blocked[9], sub_blocked[9];
-  uint8_t vm[CAAA_ACTIONS];   // valid_moves (persists across phases, turns: reference engine.cpp:158)
-  uint8_t use_selected, selected_action, unlucky;  // expansion mode (reference engine.cpp:156,160,163)
-  uint8_t pad_[1];
-};
 static_assert(sizeof(CaaaGameState) == 670, "GameState layout");
-static_assert(sizeof(GameSlot) % 4 == 0, "slot must be a whole number of words");
-static_assert((sizeof(GameSlot) / 4) % 2 == 1, "slot stride must be an odd number of words (bank-conflict-free)");
 
 }  // namespace caaa
