@@ -43,6 +43,24 @@ CAAA_HD uint32_t mod_small(const RunCtx cx, uint32_t byte, uint32_t n) {
   return byte - q * n;
 }
 
+// next non-empty cell of a phase's cell list at or after `cell` (DevTables::scan); `fresh` is raised when the
+// cursor moves on, exactly where the reference's for-loops would start a new (type, location, state) block
+CAAA_HD uint32_t scan_cells(const Game* g, const uint32_t* tab, int n_cells, int& cell, bool& fresh) {
+  const uint8_t* gb = reinterpret_cast<const uint8_t*>(g);
+  uint32_t c = 0;
+#pragma unroll 1
+  for (; cell < n_cells; cell++) {  // (a 4-wide variant with independent loads was measured: 4 % slower)
+    c = tab[cell];
+    if (gb[c & 1023u] != 0) break;
+    fresh = true;
+  }
+  return c;
+}
+CAAA_HD int cell_type(uint32_t c) { return (int)((c >> 10) & 15u); }
+CAAA_HD int cell_loc(uint32_t c) { return (int)((c >> 14) & 7u); }
+CAAA_HD int cell_state(uint32_t c) { return (int)((c >> 17) & 7u); }
+CAAA_HD uint8_t* cell_arr(Game* g, uint32_t c) { return reinterpret_cast<uint8_t*>(g) + (c & 1023u) - cell_state(c); }
+
 // ---- cache refresh, engine.cpp:642-814 ----
 CAAA_HD_NOINLINE void refresh_eot_cache(Game* g, const RunCtx cx) {  // 653-660 (refresh_allies is tabulated)
   const CaaaTables& t = CAAA_TAB(cx)->t;
@@ -366,13 +384,8 @@ CAAA_HD_NOINLINE int move_fighter_units(Game* g, const RunCtx cx, unsigned min, 
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-#pragma unroll 1
-    for (; src < NA; src++) {
-      arr = air_fighters(g, src);
-      if (arr[4] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_FIGHTERS, SC_FIGHTERS_N, src, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
     converge<!EXPAND>(mact);
     if (src >= NA) {
       active = false;
@@ -505,13 +518,8 @@ CAAA_HD_NOINLINE int move_bomber_units(Game* g, const RunCtx cx, unsigned min, i
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-#pragma unroll 1
-    for (; src < NL; src++) {
-      arr = lu_ptr(g, src, BOMBERS_LAND_AIR);
-      if (arr[6] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_BOMBERS, SC_BOMBERS_N, src, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
     converge<!EXPAND>(mact);
     if (src >= NL) {
       active = false;
@@ -597,17 +605,9 @@ CAAA_HD_NOINLINE int stage_transport_units(Game* g, const RunCtx cx, unsigned mi
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-    int ut = 0, s = 0, staging = 0;
-#pragma unroll 1
-    for (; cell < 4 * NS; cell++) {
-      ut = TRANS_EMPTY + cell / NS;
-      s = cell % NS;
-      staging = (int)states_sea(ut) - 1;
-      arr = su_ptr(g, s, ut);
-      if (arr[staging] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_STAGE, SC_STAGE_N, cell, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
+    const int ut = cell_type(cc), s = cell_loc(cc), staging = cell_state(cc);
     converge<!EXPAND>(mact);
     if (cell >= 4 * NS) {
       active = false;
@@ -676,6 +676,7 @@ CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min,
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
   const int mm = max_move_land(ut);
+  const int sc_first = ut == TANKS ? (int)SC_TANKS : ut == ARTILLERY ? (int)SC_ARTILLERY : ut == INFANTRY ? (int)SC_INFANTRY : (int)SC_AA_GUNS;
   bool processed = false, fresh = true;
   int cell = 0;  // src * mm + (mm - moves)
   if (g->cur_phase == ph) {
@@ -690,16 +691,9 @@ CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min,
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-    int src = 0, moves = 0;
-#pragma unroll 1
-    for (; cell < NL * mm; cell++) {
-      src = cell >> (mm - 1);  // mm is 1 or 2
-      moves = mm - (cell & (mm - 1));
-      arr = lu_ptr(g, src, ut);
-      if (arr[moves] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + sc_first, NL * mm, cell, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
+    const int src = cell_loc(cc), moves = cell_state(cc);
     converge<!EXPAND>(mact);
     if (cell >= NL * mm) {
       active = false;
@@ -795,17 +789,9 @@ CAAA_HD_NOINLINE int move_transport_units(Game* g, const RunCtx cx, unsigned min
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-    int ut = 0, s = 0, cs = 0;
-#pragma unroll 1
-    for (; cell < 6 * NS * 2; cell++) {
-      ut = TRANS_1I + cell / (NS * 2);
-      s = (cell / 2) % NS;
-      cs = 3 - (cell & 1);  // max_state - i, i = 1, 2
-      arr = su_ptr(g, s, ut);
-      if (arr[cs] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_TRANSPORTS, SC_TRANSPORTS_N, cell, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
+    const int ut = cell_type(cc), s = cell_loc(cc), cs = cell_state(cc);  // cs = max_state - i, i = 1, 2
     converge<!EXPAND>(mact);
     if (cell >= 6 * NS * 2) {
       active = false;
@@ -973,17 +959,9 @@ CAAA_HD_NOINLINE int move_destroyers_battleships(Game* g, const RunCtx cx, unsig
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-    int ut = 0, s = 0, unmoved = 0;
-#pragma unroll 1
-    for (; cell < 5 * NS; cell++) {
-      ut = DESTROYERS + cell / NS;
-      s = cell % NS;
-      unmoved = unmoved_sea(ut);
-      arr = su_ptr(g, s, ut);
-      if (arr[unmoved] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_SHIPS, SC_SHIPS_N, cell, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
+    const int ut = cell_type(cc), s = cell_loc(cc), unmoved = cell_state(cc);
     converge<!EXPAND>(mact);
     if (cell >= 5 * NS) {
       active = false;
@@ -1404,16 +1382,9 @@ CAAA_HD_NOINLINE int unload_transports(Game* g, const RunCtx cx, unsigned min, i
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-    int ut = 0, s = 0;
-#pragma unroll 1
-    for (; cell < 6 * NS; cell++) {
-      ut = TRANS_1I + cell / NS;
-      s = cell % NS;
-      arr = su_ptr(g, s, ut);
-      if (arr[1] != 0) break;  // STATES_UNLOADING is 1 for every loaded transport type
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_UNLOAD, SC_UNLOAD_N, cell, fresh);
+    uint8_t* const arr = cell_arr(g, cc);  // STATES_UNLOADING is 1 for every loaded transport type
+    const int ut = cell_type(cc), s = cell_loc(cc);
     converge<!EXPAND>(mact);
     if (cell >= 6 * NS) {
       active = false;
@@ -1699,16 +1670,9 @@ CAAA_HD_NOINLINE int land_fighter_units(Game* g, const RunCtx cx, unsigned min, 
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-    int src = 0, cs = 0;
-#pragma unroll 1
-    for (; cell < 3 * NA; cell++) {
-      cs = 1 + cell / NA;
-      src = cell % NA;
-      arr = air_fighters(g, src);
-      if (arr[cs] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_LAND_FIGHTERS, SC_LAND_FIGHTERS_N, cell, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
+    const int src = cell_loc(cc), cs = cell_state(cc);
     converge<!EXPAND>(mact);
     if (cell >= 3 * NA) {
       active = false;
@@ -1792,16 +1756,9 @@ CAAA_HD_NOINLINE int land_bomber_units(Game* g, const RunCtx cx, unsigned min, i
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    uint8_t* arr = nullptr;
-    int src = 0, cs = 0;
-#pragma unroll 1
-    for (; cell < 5 * NA; cell++) {
-      src = cell % NA;
-      cs = src < NL ? cell / NA + 1 : cell / NA;
-      arr = air_bombers(g, src);
-      if (arr[cs] != 0) break;
-      fresh = true;
-    }
+    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + SC_LAND_BOMBERS, SC_LAND_BOMBERS_N, cell, fresh);
+    uint8_t* const arr = cell_arr(g, cc);
+    const int src = cell_loc(cc), cs = cell_state(cc);
     converge<!EXPAND>(mact);
     if (cell >= 5 * NA) {
       active = false;

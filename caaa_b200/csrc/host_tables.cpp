@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "host_tables.h"
+#include "game.cuh"
 
 namespace caaa {
 namespace {
@@ -157,6 +158,48 @@ void build_dev_tables(DevTables* out) {
   std::memset(out, 0, sizeof(*out));
   build_tables(&out->t);
   for (uint32_t n = 1; n < 32; n++) out->recip16[n] = 65536u / n + 1u;
+  {  // cell lists of the move phases (reference loop orders, src/engine.cpp:1593-1599, 1734, 1998, 2088-2098, ...)
+    using e2::Game;
+    auto land_cell = [](int l, int ut, int st) { return (uint32_t)(offsetof(Game, lu) + l * e2::LU_ROW + e2::off_lu(ut) + st); };
+    auto sea_cell = [](int sea, int ut, int st) { return (uint32_t)(offsetof(Game, su) + sea * e2::SU_ROW + off_sea(ut) + st); };
+    auto pack = [](uint32_t off, int ut, int loc, int st) { return off | ((uint32_t)ut << 10) | ((uint32_t)loc << 14) | ((uint32_t)st << 17); };
+    uint32_t* t = out->scan;
+    for (int a = 0; a < NA; a++)
+      t[SC_FIGHTERS + a] = pack(a < NL ? land_cell(a, FIGHTERS, 4) : sea_cell(a - NL, FIGHTERS, 4), FIGHTERS, a, 4);
+    for (int l = 0; l < NL; l++) t[SC_BOMBERS + l] = pack(land_cell(l, BOMBERS_LAND_AIR, 6), BOMBERS_LAND_AIR, l, 6);
+    for (int ut = TRANS_EMPTY; ut <= TRANS_1T; ut++)
+      for (int sea = 0; sea < NS; sea++) {
+        const int st = (int)states_sea(ut) - 1;
+        t[SC_STAGE + (ut - TRANS_EMPTY) * NS + sea] = pack(sea_cell(sea, ut, st), ut, sea, st);
+      }
+    for (int l = 0; l < NL; l++) {
+      t[SC_TANKS + l * 2 + 0] = pack(land_cell(l, TANKS, 2), TANKS, l, 2);
+      t[SC_TANKS + l * 2 + 1] = pack(land_cell(l, TANKS, 1), TANKS, l, 1);
+      t[SC_ARTILLERY + l] = pack(land_cell(l, ARTILLERY, 1), ARTILLERY, l, 1);
+      t[SC_INFANTRY + l] = pack(land_cell(l, INFANTRY, 1), INFANTRY, l, 1);
+      t[SC_AA_GUNS + l] = pack(land_cell(l, AA_GUNS, 1), AA_GUNS, l, 1);
+    }
+    for (int ut = TRANS_1I; ut <= TRANS_1I_1T; ut++)
+      for (int sea = 0; sea < NS; sea++) {
+        for (int i = 1; i <= 2; i++)
+          t[SC_TRANSPORTS + ((ut - TRANS_1I) * NS + sea) * 2 + (i - 1)] = pack(sea_cell(sea, ut, 4 - i), ut, sea, 4 - i);
+        t[SC_UNLOAD + (ut - TRANS_1I) * NS + sea] = pack(sea_cell(sea, ut, 1), ut, sea, 1);
+      }
+    for (int ut = DESTROYERS; ut <= BS_DAMAGED; ut++)
+      for (int sea = 0; sea < NS; sea++) {
+        const int st = (int)unmoved_sea(ut);
+        t[SC_SHIPS + (ut - DESTROYERS) * NS + sea] = pack(sea_cell(sea, ut, st), ut, sea, st);
+      }
+    for (int st = 1; st <= 3; st++)
+      for (int a = 0; a < NA; a++)
+        t[SC_LAND_FIGHTERS + (st - 1) * NA + a] = pack(a < NL ? land_cell(a, FIGHTERS, st) : sea_cell(a - NL, FIGHTERS, st), FIGHTERS, a, st);
+    for (int c1 = 0; c1 < 5; c1++)
+      for (int a = 0; a < NA; a++) {
+        const int st = a < NL ? c1 + 1 : c1;
+        t[SC_LAND_BOMBERS + c1 * NA + a] =
+            pack(a < NL ? land_cell(a, BOMBERS_LAND_AIR, st) : sea_cell(a - NL, BOMBERS_SEA, st), a < NL ? (int)BOMBERS_LAND_AIR : (int)BOMBERS_SEA, a, st);
+      }
+  }
   for (int pi = 0; pi < NP; pi++) {  // refresh_allies (engine.cpp:716-725) for every player to move
     for (int p = 0; p < NP; p++) {
       if (out->t.is_allied[pi][(pi + p) % NP]) out->allied_mask[pi] |= (uint8_t)(1u << p);

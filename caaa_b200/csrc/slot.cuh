@@ -80,6 +80,23 @@ CAAA_HD constexpr uint32_t order_sea_att3(int k) {
 }
 CAAA_HD constexpr uint32_t buy_sea(int k) { return pk8(k, CAAA_PK(FIGHTERS, TRANS_EMPTY, SUBMARINES, DESTROYERS, CARRIERS, CRUISERS, BATTLESHIPS, 0)); }
 
+// sections of DevTables::scan
+enum : int {
+  SC_FIGHTERS = 0, SC_FIGHTERS_N = 8,
+  SC_BOMBERS = SC_FIGHTERS + SC_FIGHTERS_N, SC_BOMBERS_N = 5,
+  SC_STAGE = SC_BOMBERS + SC_BOMBERS_N, SC_STAGE_N = 12,
+  SC_TANKS = SC_STAGE + SC_STAGE_N, SC_TANKS_N = 10,
+  SC_ARTILLERY = SC_TANKS + SC_TANKS_N, SC_ARTILLERY_N = 5,
+  SC_INFANTRY = SC_ARTILLERY + SC_ARTILLERY_N, SC_INFANTRY_N = 5,
+  SC_AA_GUNS = SC_INFANTRY + SC_INFANTRY_N, SC_AA_GUNS_N = 5,
+  SC_TRANSPORTS = SC_AA_GUNS + SC_AA_GUNS_N, SC_TRANSPORTS_N = 36,
+  SC_SHIPS = SC_TRANSPORTS + SC_TRANSPORTS_N, SC_SHIPS_N = 15,
+  SC_UNLOAD = SC_SHIPS + SC_SHIPS_N, SC_UNLOAD_N = 18,
+  SC_LAND_FIGHTERS = SC_UNLOAD + SC_UNLOAD_N, SC_LAND_FIGHTERS_N = 24,
+  SC_LAND_BOMBERS = SC_LAND_FIGHTERS + SC_LAND_FIGHTERS_N, SC_LAND_BOMBERS_N = 40,
+  SCAN_TOTAL = SC_LAND_BOMBERS + SC_LAND_BOMBERS_N
+};
+
 // Read-only tables staged once per CTA in shared memory: the reference's topology tables plus
 // per-player-to-move team lists (refresh_allies, reference src/engine.cpp:716-725, depends only
 // on player_index, so it is tabulated instead of cached per game).
@@ -94,6 +111,10 @@ struct DevTables {
   uint8_t enemies_abs[NP][4]; // absolute ids of the enemies, in the relative order above
   uint8_t pad2_[3];
   uint32_t recip16[32];       // ceil(2^16 / n): byte % n without a division (n = 0 is never used)
+  // Cell lists of the move phases, in the reference's loop order: one entry per (unit type, location, movement
+  // state) a phase looks at = byte offset of that count inside a Game (bits 0..9) | type << 10 | location << 14 |
+  // state << 17.  Finding the next non-empty cell is then one table read + one byte read per cell.
+  uint32_t scan[SCAN_TOTAL];
 };
 
 // status bits reported per game (0 = clean)
