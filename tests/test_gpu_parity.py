@@ -116,6 +116,46 @@ def test_expansion_golden(eng):
         assert (status[i] != 0) == bool(g["stuck"][i][:n].any()), i
 
 
+def test_ragged_batches_vs_oracle(eng, port):
+    """Batch shapes around the kernel's internal sizes (32 lanes, 224 slots per SM, 16 games per warp): one game,
+    partial warps, partial CTAs, several start states with one or a few playouts each."""
+    s0 = layout.start_state()
+    seed = 0xBA7C4
+    port.set_stream(1, seed)
+    first = 123456
+    for n in (1, 2, 15, 17, 31, 33, 223, 225, 449):
+        _, got, summ = eng.rollout_batch(s0, n, seed, first, want_stats=True)
+        assert np.array_equal(got, port.rollout_many(s0, first, n)), n
+        assert summ["playouts"] == n
+        first += n
+    a = np.load(os.path.join(GOLD, "advance.npz"))
+    states = a["states"][:37]
+    for per in (1, 3):
+        _, got, _ = eng.rollout_batch(states, per, seed, 999, want_stats=True)
+        want = np.concatenate([port.rollout_many(states[i], 999 + i * per, per) for i in range(len(states))])
+        assert np.array_equal(got, want), per
+
+
+def test_lockstep_and_regrouped_kernels_agree(tmp_path):
+    """The walk-the-pipeline kernel (CAAA_ROLLOUT_KERNEL=lockstep, with and without the per-phase CTA barrier) and the
+    phase-regrouped kernel with other warp widths play the same playouts bit for bit (separate processes: the
+    library reads its knobs once at init)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from caaa_b200 import gpu, layout; "
+            "e = gpu.GpuEngine(0); r, s, _ = e.rollout_batch(layout.start_state(), 3000, 0xABCD, 5, want_stats=True); "
+            "np.save(sys.argv[1], s)" % root)
+    outs = []
+    for k, env in enumerate(({}, {"CAAA_ROLLOUT_KERNEL": "lockstep"}, {"CAAA_ROLLOUT_KERNEL": "lockstep", "CAAA_SYNC": "1"},
+                             {"CAAA_LANES": "32", "CAAA_GROUP": "1"}, {"CAAA_LANES": "8", "CAAA_YIELD": "75"})):
+        out = str(tmp_path / f"k{k}.npy")
+        subprocess.check_call([sys.executable, "-c", code, out], env={**os.environ, **env})
+        outs.append(np.load(out))
+    for o in outs[1:]:
+        assert np.array_equal(outs[0], o)
+
+
 def test_single_playout_shim(eng):
     g = np.load(os.path.join(GOLD, "start_rollouts.npz"))
     eng.set_stream(int(g["seed"]), 0)
