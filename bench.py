@@ -39,7 +39,7 @@ KERNELS_PER_BATCH = 3
 ROLLOUT_KERNEL = "rollout_kernel_stream<false, 16>"
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_kernel_stream launch of 2**20 playouts
 # (profiles/r1_ncu_summary.md); None when this run uses another batch size
-NCU_DRAM_BYTES_PER_1M_LAUNCH = None
+NCU_DRAM_BYTES_PER_1M_LAUNCH = 57_682_444_032  # 7.4 MB read + 57.7 GB written (profiles/dram_r1_pool2.csv)
 
 
 def measured_peaks():
@@ -261,7 +261,7 @@ def ours(args):
                                    "(game_data.json), bit-exact vs the patched reference",
                        "playouts_per_gpu_per_step": P, "seed": SEED, "plies_per_sec": plies_total / total_s,
                        "plies_per_playout": plies_total / (world * P * args.steps), "flagged_playouts": float(flagged.item()),
-                       "l2": "256 MiB write between timed steps (untimed); the game pool (~100 MB) is rewritten by every step",
+                       "l2": "256 MiB write between timed steps (untimed); the 62 MB game pool is re-initialised by every step",
                        "sharding": "game-id ranges per rank, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if P == (1 << 20) else None, "peak_source": peak_src,

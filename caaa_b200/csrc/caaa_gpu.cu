@@ -381,7 +381,7 @@ struct Context {
   unsigned long long seed = 0, next_game_id = 0;
   bool sync_phases = false;  // CAAA_SYNC=1: CTA barrier after every phase (A/B knob)
   bool streaming = true;     // CAAA_ROLLOUT_KERNEL=lockstep selects the walk-the-pipeline kernel instead
-  int pool_mult = 3;         // pool entries per shared-memory slot (CAAA_POOL_MULT)
+  int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
   int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
   int group_size = 16;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
   void* d_pool = nullptr;    // per-SM game pools of the phase-regrouped kernel
@@ -450,7 +450,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.ticket = c.d_ticket;
   {
     const char* sb = std::getenv("CAAA_SWITCH_BELOW");
-    a.switch_below = sb ? std::atoi(sb) : 16;
+    a.switch_below = sb ? std::atoi(sb) : 8;
     const char* yl = std::getenv("CAAA_YIELD");
     a.yield_lanes = yl ? std::atoi(yl) : 0;
     const char* sr = std::getenv("CAAA_SCAN_ROUNDS");
@@ -537,7 +537,7 @@ int caaa_gpu_init(int device) {
   const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
   c.streaming = !(rk != nullptr && std::strcmp(rk, "lockstep") == 0);
   const char* pm = std::getenv("CAAA_POOL_MULT");
-  c.pool_mult = pm ? std::atoi(pm) : 3;
+  c.pool_mult = pm ? std::atoi(pm) : 2;
   if (c.pool_mult < 1) c.pool_mult = 1;
   if (c.pool_mult > MAX_POOL_MULT) c.pool_mult = MAX_POOL_MULT;
   const char* ln = std::getenv("CAAA_LANES");
