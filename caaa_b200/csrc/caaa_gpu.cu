@@ -384,8 +384,10 @@ struct Context {
   int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
   int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
   int group_size = 16;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
-  void* d_pool = nullptr;    // per-SM game pools of the phase-regrouped kernel
+  void* d_pool = nullptr;    // game pools + group state of the phase-regrouped kernel
   size_t pool_cap = 0;
+  GroupState* d_groups_last = nullptr;  // group state of the most recent launch (watchdog flag)
+  int n_groups_last = 0;
 };
 static Context g_ctx;
 static std::string g_err;
@@ -482,6 +484,8 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     if (c.lanes == 32) CAAA_LAUNCH_STREAM(32);
     else if (c.lanes == 8) CAAA_LAUNCH_STREAM(8);
     else CAAA_LAUNCH_STREAM(16);
+    c.d_groups_last = d_groups;
+    c.n_groups_last = n_groups;
     if (d_dbg != nullptr) {
       StreamDbg h;
       cudaStreamSynchronize(stream);
@@ -638,6 +642,12 @@ int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollou
   CaaaBatchSummary s;
   CUDA_TRY(cudaMemcpyAsync(&s, c.d_summary, sizeof(s), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
+  for (int gidx = 0; c.streaming && gidx < c.n_groups_last; gidx++) {  // watchdog of the phase-regrouped kernel
+    int aborted = 0;
+    CUDA_TRY(cudaMemcpy(&aborted, &c.d_groups_last[gidx].aborted, sizeof(int), cudaMemcpyDeviceToHost));
+    if (aborted) return fail(CAAA_E_CUDA, "rollout kernel stopped by its watchdog: no claimable game although the batch was unfinished");
+  }
+  if (s.playouts != (unsigned long long)n_games) return fail(CAAA_E_CUDA, "rollout kernel finished fewer playouts than requested");
   if (summary) {
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, c.ev0, c.ev1));

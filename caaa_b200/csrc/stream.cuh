@@ -40,7 +40,8 @@ struct GroupState {
   int cnt[NQ];                      // their number (selection heuristic; the bitmaps are the truth)
   int servers[NQ];                  // CTAs currently serving each phase
   int retired;                      // pool entries that found no ticket left
-  int pad_[3];
+  int aborted;                      // set by a warp that saw no work for seconds although games are left (watchdog)
+  int pad_[2];
 };
 struct StreamShared {
   int kind;                       // the phase this CTA currently serves
@@ -63,7 +64,10 @@ __global__ void group_init_kernel(GroupState* G, int n_groups, int entries_per_c
     gs->cnt[threadIdx.x] = threadIdx.x == Q_FREE ? pool_g : 0;
     gs->servers[threadIdx.x] = 0;
   }
-  if (threadIdx.x == 0) gs->retired = 0;
+  if (threadIdx.x == 0) {
+    gs->retired = 0;
+    gs->aborted = 0;
+  }
 }
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
@@ -113,6 +117,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   constexpr unsigned LANE_MASK = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
   constexpr int KW = (GAME_WORDS + 31) / 32;
   LaneTotals tot;
+  long long last_work = clock64();
   unsigned long long d_batches = 0, d_items = 0, d_t[6] = {0, 0, 0, 0, 0, 0};
   long long d_c0 = clock64();
 #define CAAA_LAP(k)                                   \
@@ -179,6 +184,13 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       const unsigned key = __reduce_max_sync(FULL, score ? (score << 5) | (unsigned)lane : 0u);
       if (key == 0) {
         if (*vretired >= pool_n) break;  // every pool entry has retired: the batch is done
+        // watchdog: games are left but nothing has been claimable for ~4 s -- give up rather than hang the GPU;
+        // the host reports the failure (it would mean a lost pool entry, i.e. a bug in this scheduler)
+        if (*reinterpret_cast<volatile int*>(&GS->aborted)) break;
+        if (clock64() - last_work > 8000000000LL) {
+          if (lane == 0) atomicExch(&GS->aborted, 1);
+          break;
+        }
         __nanosleep(200);
         continue;
       }
@@ -204,6 +216,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       first = false;
       CAAA_LAP(0);  // idle + select + claim
       if (n_new > 0) {
+        last_work = clock64();
         d_batches++;
         d_items += (unsigned)n_new;
         __threadfence();
