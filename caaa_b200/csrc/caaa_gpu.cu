@@ -79,7 +79,7 @@ struct LaneTotals {
 };
 
 template <bool STATS>
-__device__ __forceinline__ void finish_playout(Game* g, double score, unsigned long long gi, const RolloutArgs& a, LaneTotals& tot) {
+__device__ __noinline__ void finish_playout(Game* g, double score, unsigned long long gi, const RolloutArgs& a, LaneTotals& tot) {
   const double r = (g->player % 2 == 1) ? 1.0 - score : score;  // reference src/engine.cpp:4238-4241
   a.results[gi] = r;
   const int decisions = 100000 - g->answers_remaining;

@@ -84,6 +84,55 @@ struct StreamDbg {
   unsigned long long batches, items, t[6];
 };
 
+// (Re)start the pool entries of the lanes with `need_start` from the batch's ticket counter: one fetch per warp,
+// cooperative copy of the pre-imported start state.  Lanes that find no ticket left retire their entry.
+template <bool STATS>
+__device__ __noinline__ void restart_lanes(const RolloutArgs& a, Game* warp_games, Game* g, int lane, bool one_state, bool& need_start,
+                                           bool& live, bool& retired, LaneTotals& tot) {
+  constexpr int KW = (GAME_WORDS + 31) / 32;
+  for (;;) {
+    const unsigned need = __ballot_sync(FULL, need_start);
+    if (need == 0) break;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.ticket, (unsigned long long)__popc(need));
+    base = __shfl_sync(FULL, base, 0);
+    unsigned m = need;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const unsigned long long gj = base + (unsigned)__popc(need & ((1u << j) - 1u));
+      if (gj < a.n_games) {
+        const unsigned long long sj = one_state ? 0ULL : gj / a.rollouts_per_state;
+        const uint32_t* src = a.templates + sj * GAME_WORDS;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + j);
+#pragma unroll 1
+        for (int k = 0; k < KW; k++)
+          if (k * 32 + lane < GAME_WORDS) cp_async4(dst + k * 32 + lane, src + k * 32 + lane);
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    if (need_start) {
+      const unsigned long long gi = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+      if (gi < a.n_games) {
+        const unsigned long long id = a.first_game_id + gi;
+        g->game_lo = (uint32_t)id;
+        g->game_hi = (uint32_t)(id >> 32);
+        const double score = a.scores0[one_state ? 0ULL : gi / a.rollouts_per_state];
+        if (score > 0.01 && score < 0.99) {
+          live = true;
+          need_start = false;
+        } else {
+          finish_playout<STATS>(g, score, gi, a, tot);  // already terminal: zero turns, take another ticket
+        }
+      } else {
+        need_start = false;
+        retired = true;
+      }
+    }
+  }
+}
+
 // LANES = games per warp.  A warp serves ONE phase at a time: it claims games waiting for that phase, runs the
 // phase on them in lockstep, and -- because the work per game is heavy-tailed -- lets the phase YIELD as soon as a
 // quarter of its lanes are done: the finished games are routed on, their lanes are refilled with other games
@@ -309,49 +358,10 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       }
       __syncwarp();
       CAAA_LAP(2);  // compute
-      // ---- (re)start pool entries from the ticket counter: one fetch per warp, cooperative copy of the start state ----
+      // ---- (re)start pool entries from the ticket counter (out of line: it runs once per playout, and the hot loop of
+      // this kernel should stay small in the instruction cache) ----
       bool retired = false;
-      for (;;) {
-        const unsigned need = __ballot_sync(FULL, need_start);
-        if (need == 0) break;
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(a.ticket, (unsigned long long)__popc(need));
-        base = __shfl_sync(FULL, base, 0);
-        unsigned m = need;
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const unsigned long long gj = base + (unsigned)__popc(need & ((1u << j) - 1u));
-          if (gj < a.n_games) {
-            const unsigned long long sj = one_state ? 0ULL : gj / a.rollouts_per_state;
-            const uint32_t* src = a.templates + sj * GAME_WORDS;
-            uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + j);
-#pragma unroll
-            for (int k = 0; k < KW; k++)
-              if (k * 32 + lane < GAME_WORDS) cp_async4(dst + k * 32 + lane, src + k * 32 + lane);
-          }
-        }
-        cp_async_wait_all();
-        __syncwarp();
-        if (need_start) {
-          const unsigned long long gi = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-          if (gi < a.n_games) {
-            const unsigned long long id = a.first_game_id + gi;
-            g->game_lo = (uint32_t)id;
-            g->game_hi = (uint32_t)(id >> 32);
-            const double score = a.scores0[one_state ? 0ULL : gi / a.rollouts_per_state];
-            if (score > 0.01 && score < 0.99) {
-              live = true;
-              need_start = false;
-            } else {
-              finish_playout<STATS>(g, score, gi, a, tot);  // already terminal: zero turns, take another ticket
-            }
-          } else {
-            need_start = false;
-            retired = true;
-          }
-        }
-      }
+      if (__any_sync(FULL, need_start)) restart_lanes<STATS>(a, warp_games, g, lane, one_state, need_start, live, retired, tot);
       CAAA_LAP(3);  // restart
       // ---- route every finished game to the next phase that has work for it and copy it back out; games that
       // yielded stay in their slots ----
