@@ -176,3 +176,39 @@ extern "C" void caaa_hostsim_rollout_many_sliced(const void* s, int64_t first, i
 extern "C" void caaa_hostsim_rollout_many_routed(const void* s, int64_t first, int n, CaaaRolloutStats* st) {
   caaa_hostsim_rollout_many_sliced(s, first, n, 1, st);
 }
+// iteration statistics of the phase loops (tools only): runs `n` playouts and, for every phase call that had work,
+// adds one sample (phase, units waiting in the phase's cells at entry, loop iterations) to the caller's arrays
+extern "C" int caaa_hostsim_phase_stats(const void* s, int64_t first, int n, int32_t* out, int cap) {
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    Game* g = &g_game;
+    import_state(g, (const uint8_t*)s);
+    begin_playout(g, g_cx, (uint64_t)first + (uint64_t)i);
+    double score = evaluate_state(g, g_cx);
+    while (score > 0.01 && score < 0.99 && g->turns < 1000) {
+      for (int ph = 0; ph < CAAA_PH_COUNT; ph++) {
+        const bool has = ph <= CAAA_PH_BUY_UNITS && (ph == CAAA_PH_BUY_UNITS || (g->work >> ph) & 1u);
+        int units = 0;
+        if (has && ph < CAAA_PH_BUY_UNITS) {
+          static const int sec[15][2] = {{SC_FIGHTERS, SC_FIGHTERS_N}, {SC_BOMBERS, SC_BOMBERS_N}, {SC_STAGE, SC_STAGE_N}, {SC_TANKS, SC_TANKS_N},
+                                         {SC_ARTILLERY, SC_ARTILLERY_N}, {SC_INFANTRY, SC_INFANTRY_N}, {SC_TRANSPORTS, SC_TRANSPORTS_N}, {-1, 0},
+                                         {SC_SHIPS, SC_SHIPS_N}, {-1, 0}, {SC_UNLOAD, SC_UNLOAD_N}, {-1, 0}, {SC_AA_GUNS, SC_AA_GUNS_N},
+                                         {SC_LAND_FIGHTERS, SC_LAND_FIGHTERS_N}, {SC_LAND_BOMBERS, SC_LAND_BOMBERS_N}};
+          if (sec[ph][0] >= 0)
+            for (int c = 0; c < sec[ph][1]; c++) units += ((const uint8_t*)g)[g_tables.scan[sec[ph][0] + c] & 1023u];
+        }
+        if (ph == CAAA_PH_BUY_UNITS) units = g->money[g->cur];
+        int iters = 1;
+        while (run_phase<false>(g, g_cx, ph, 0xffffffffu, 1) == PH_YIELDED) iters++;
+        if (has && k + 3 <= cap) {
+          out[k++] = ph;
+          out[k++] = units;
+          out[k++] = iters;
+        }
+      }
+      g->turns++;
+      score = evaluate_state(g, g_cx);
+    }
+  }
+  return k / 3;
+}
