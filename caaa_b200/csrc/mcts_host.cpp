@@ -97,7 +97,7 @@ extern "C" int caaa_mcts_search(const CaaaGameState* root_state, int64_t iterati
       Node* leaf = select_best_leaf(root);
       if (leaf->in_batch) break;  // the tree offers no further distinct leaf right now
       leaf->in_batch = true;
-      for (Node* n = leaf; n != nullptr; n = n->parent) n->pending++;
+      for (Node* n = leaf; n != nullptr; n = n->parent) n->pending += rollouts_per_leaf;  // one visit = rollouts_per_leaf playouts
       leaves.push_back(leaf);
     }
     const int nl = (int)leaves.size();
@@ -133,7 +133,7 @@ extern "C" int caaa_mcts_search(const CaaaGameState* root_state, int64_t iterati
     next_game_id += (uint64_t)nl * (uint64_t)rollouts_per_leaf;
     // 4. clear the virtual visits and back-propagate
     for (int i = 0; i < nl; i++) {
-      for (Node* n = leaves[i]; n != nullptr; n = n->parent) n->pending--;
+      for (Node* n = leaves[i]; n != nullptr; n = n->parent) n->pending -= rollouts_per_leaf;
       leaves[i]->in_batch = false;
       double sum = 0.0;
       for (int r = 0; r < rollouts_per_leaf; r++) sum += results[(size_t)i * rollouts_per_leaf + r];
