@@ -381,6 +381,8 @@ struct Context {
   unsigned long long seed = 0, next_game_id = 0;
   bool sync_phases = false;  // CAAA_SYNC=1: CTA barrier after every phase (A/B knob)
   bool streaming = true;     // CAAA_ROLLOUT_KERNEL=lockstep selects the walk-the-pipeline kernel instead
+  long long small_batch = 32768;  // batches up to this size go to the lockstep kernel (no pool hops: lower latency);
+                                  // CAAA_ROLLOUT_KERNEL=stream sets it to 0
   int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
   int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
   int group_size = 16;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
@@ -461,7 +463,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   }
   const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
   const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
-  if (c.streaming) {
+  if (c.streaming && (long long)n_games > c.small_batch) {
     const size_t need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game);
     const int n_groups = (grid + c.group_size - 1) / c.group_size;
     const size_t need16 = (need + 15) / 16 * 16;
@@ -540,6 +542,7 @@ int caaa_gpu_init(int device) {
   c.sync_phases = sy != nullptr && std::atoi(sy) != 0;
   const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
   c.streaming = !(rk != nullptr && std::strcmp(rk, "lockstep") == 0);
+  if (rk != nullptr && std::strcmp(rk, "stream") == 0) c.small_batch = 0;
   const char* pm = std::getenv("CAAA_POOL_MULT");
   c.pool_mult = pm ? std::atoi(pm) : 2;
   if (c.pool_mult < 1) c.pool_mult = 1;
@@ -642,7 +645,7 @@ int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollou
   CaaaBatchSummary s;
   CUDA_TRY(cudaMemcpyAsync(&s, c.d_summary, sizeof(s), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
-  for (int gidx = 0; c.streaming && gidx < c.n_groups_last; gidx++) {  // watchdog of the phase-regrouped kernel
+  for (int gidx = 0; c.streaming && (long long)n_games > c.small_batch && gidx < c.n_groups_last; gidx++) {  // watchdog of the phase-regrouped kernel
     int aborted = 0;
     CUDA_TRY(cudaMemcpy(&aborted, &c.d_groups_last[gidx].aborted, sizeof(int), cudaMemcpyDeviceToHost));
     if (aborted) return fail(CAAA_E_CUDA, "rollout kernel stopped by its watchdog: no claimable game although the batch was unfinished");

@@ -116,6 +116,22 @@ def test_expansion_golden(eng):
         assert (status[i] != 0) == bool(g["stuck"][i][:n].any()), i
 
 
+def test_regrouped_kernel_small_batches_vs_oracle(port, tmp_path):
+    """Small batches default to the lockstep kernel; force the phase-regrouped kernel through the same ragged shapes."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from caaa_b200 import gpu, layout; e = gpu.GpuEngine(0); "
+            "out = [e.rollout_batch(layout.start_state(), n, 0xBA7C4, 1000 * n, want_stats=True)[1] for n in (1, 2, 17, 33, 225, 449)]; "
+            "np.save(sys.argv[1], np.concatenate(out))" % root)
+    out = str(tmp_path / "s.npy")
+    subprocess.check_call([sys.executable, "-c", code, out], env={**os.environ, "CAAA_ROLLOUT_KERNEL": "stream"})
+    port.set_stream(1, 0xBA7C4)
+    s0 = layout.start_state()
+    want = np.concatenate([port.rollout_many(s0, 1000 * n, n) for n in (1, 2, 17, 33, 225, 449)])
+    assert np.array_equal(np.load(out), want)
+
+
 def test_ragged_batches_vs_oracle(eng, port):
     """Batch shapes around the kernel's internal sizes (32 lanes, 224 slots per SM, 16 games per warp): one game,
     partial warps, partial CTAs, several start states with one or a few playouts each."""
@@ -147,8 +163,10 @@ def test_lockstep_and_regrouped_kernels_agree(tmp_path):
             "e = gpu.GpuEngine(0); r, s, _ = e.rollout_batch(layout.start_state(), 3000, 0xABCD, 5, want_stats=True); "
             "np.save(sys.argv[1], s)" % root)
     outs = []
-    for k, env in enumerate(({}, {"CAAA_ROLLOUT_KERNEL": "lockstep"}, {"CAAA_ROLLOUT_KERNEL": "lockstep", "CAAA_SYNC": "1"},
-                             {"CAAA_LANES": "32", "CAAA_GROUP": "1"}, {"CAAA_LANES": "8", "CAAA_YIELD": "75"})):
+    for k, env in enumerate(({"CAAA_ROLLOUT_KERNEL": "stream"}, {"CAAA_ROLLOUT_KERNEL": "lockstep"},
+                             {"CAAA_ROLLOUT_KERNEL": "lockstep", "CAAA_SYNC": "1"},
+                             {"CAAA_ROLLOUT_KERNEL": "stream", "CAAA_LANES": "32", "CAAA_GROUP": "1"},
+                             {"CAAA_ROLLOUT_KERNEL": "stream", "CAAA_LANES": "8", "CAAA_YIELD": "75"})):
         out = str(tmp_path / f"k{k}.npy")
         subprocess.check_call([sys.executable, "-c", code, out], env={**os.environ, **env})
         outs.append(np.load(out))
