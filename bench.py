@@ -38,7 +38,7 @@ METRIC = "playouts/sec"
 KERNELS_PER_BATCH = 3
 ROLLOUT_KERNEL = "rollout_kernel_stream<false, 16>"
 # dram__bytes_read.sum + dram__bytes_write.sum of one rollout_kernel_stream launch of 2**20 playouts
-# (profiles/r1_ncu_summary.md); None when this run uses another batch size
+# (profiles/dram_r1_pool2.csv, profiles/r1_ncu_summary.md); None when this run uses another batch size
 NCU_DRAM_BYTES_PER_1M_LAUNCH = 57_682_444_032  # 7.4 MB read + 57.7 GB written (profiles/dram_r1_pool2.csv)
 
 
