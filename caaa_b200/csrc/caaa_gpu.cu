@@ -55,6 +55,7 @@ struct RolloutArgs {
   int switch_below;
   int yield_lanes;   // a phase yields once this percentage of its batch is done; stragglers are requeued (0 = never)
   int scan_rounds;   // bitmap words / 32 a claim may look at
+  int yield_battles; // like yield_lanes, for the two battle phases only
 };
 
 // Import every start / leaf state once: reference layout -> Game with all derived caches, ready to be
@@ -457,6 +458,8 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     a.switch_below = sb ? std::atoi(sb) : 8;
     const char* yl = std::getenv("CAAA_YIELD");
     a.yield_lanes = yl ? std::atoi(yl) : 0;
+    const char* yb = std::getenv("CAAA_YIELD_BATTLES");
+    a.yield_battles = yb ? std::atoi(yb) : 0;
     const char* sr = std::getenv("CAAA_SCAN_ROUNDS");
     a.scan_rounds = sr ? std::atoi(sr) : 4;
     if (a.scan_rounds < 1) a.scan_rounds = 1;

@@ -307,12 +307,12 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       if (mhave == 0) break;
       // ---- run the phase on all held games in lockstep; it may yield when a quarter of the lanes are done and
       // replacements are waiting ----
-      const int waiting = __shfl_sync(FULL, lane < NQ ? vcnt[lane] : 0, kind);
-      // a_yield_pct > 0: the phase yields once that share of the batch is done; the stragglers are queued for the same
-      // phase again (cursor saved in the game) and meet other stragglers there
+      // yield_pct > 0: the phase yields once that share of the batch is done; the stragglers are queued for the same
+      // phase again (cursor saved in the game) and meet other stragglers there.  yield_battles_pct applies to the two
+      // battle phases only, whose round counts have by far the longest tail.
       const int nh = __popc(mhave);
-      const int yield = (a.yield_lanes > 0 && nh >= 8) ? (nh * a.yield_lanes + 99) / 100 : 0;
-      (void)waiting;
+      const int pct = (kind == CAAA_PH_SEA_BATTLES || kind == CAAA_PH_LAND_BATTLES) && a.yield_battles > 0 ? a.yield_battles : a.yield_lanes;
+      const int yield = (pct > 0 && nh >= 6) ? (nh * pct + 99) / 100 : 0;
       int res = PH_DONE;
       bool live = runs, need_start = false;
       if (runs) {
