@@ -165,6 +165,7 @@ def ours(args):
     import torch
     import torch.distributed as dist
     from caaa_b200 import gpu, layout
+    from caaa_b200.root_parallel import shard_first_game_id
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,7 +191,7 @@ def ours(args):
         torch.cuda.synchronize()
 
     def device_step(k):
-        eng.rollout_batch_device(d_state.data_ptr(), 1, P, SEED, (rank + world * k) * P, d_results.data_ptr(), None,
+        eng.rollout_batch_device(d_state.data_ptr(), 1, P, SEED, shard_first_game_id(rank, world, k, P), d_results.data_ptr(), None,
                                  d_summary.data_ptr(), stream)
 
     # ---- value: inputs resident in HBM ----
@@ -233,7 +234,7 @@ def ours(args):
     t0 = time.perf_counter()
     e2e_steps = args.steps
     for k in range(e2e_steps):
-        res, _, _ = eng.rollout_batch(states_host, P, SEED, (rank + world * (1000 + k)) * P)
+        res, _, _ = eng.rollout_batch(states_host, P, SEED, shard_first_game_id(rank, world, 1000 + k, P))
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:

@@ -43,3 +43,10 @@ def root_parallel_search(search_fn, state, iterations_per_rank, base_seed, group
     actions, visits, values = search_fn(state, iterations_per_rank, base_seed + rank)
     actions, visits, values = combine_root_stats(actions, visits, values, group=group, device=device)
     return actions, visits, values, select_best_action(actions, values)
+
+
+def shard_first_game_id(rank, world, step, playouts_per_rank_per_step):
+    """Game-id range of one rank for one step of a sharded playout job (bench.py): ranks play disjoint,
+    contiguous id ranges, so the union over ranks and steps is exactly what one GPU would play alone -- there is no
+    data-path collective.  Returns the first id; the rank plays [first, first + playouts_per_rank_per_step)."""
+    return (rank + world * step) * playouts_per_rank_per_step

@@ -104,6 +104,34 @@ def test_battles_vs_oracle_ragged(eng, port):
         assert port.draws() == draws[i]
 
 
+def test_battle_sweep_properties(eng):
+    """BASELINE config 3 shape at a size the oracle cannot reach in seconds (1 M battles): the result of a battle is a
+    pure function of (state, seed, game id) -- identical however the sweep is batched -- battles only ever remove
+    units, and a resolved territory is no longer flagged unless the fight was broken off by a retreat decision."""
+    n = 1 << 20
+    chunk = synth.battle_states(1 << 16, seed=0xBA77)
+    bs = np.tile(chunk, (n // len(chunk), 1))
+    out, draws, summ = eng.resolve_battles(bs, 0xBA77, 0)
+    assert summ["playouts"] == n and summ["draws"] == draws.astype(np.int64).sum() and summ["flagged"] == 0
+    cut = 300_001
+    oa, da, _ = eng.resolve_battles(bs[:cut], 0xBA77, 0)
+    ob, db, _ = eng.resolve_battles(bs[cut:], 0xBA77, cut)
+    assert np.array_equal(np.concatenate([oa, ob]), out) and np.array_equal(np.concatenate([da, db]), draws)
+    # same states, other game ids -> other dice: the tiled copies of one state do not all end alike
+    k = len(chunk)
+    assert (fnv_rows(out[:k]) != fnv_rows(out[k:2 * k])).mean() > 0.3
+    # unit counts never grow (bytes 14..597 hold every unit count; owner / factory bytes may change on conquest)
+    before = bs.view(layout.STATE_DTYPE).reshape(-1)
+    after = out.view(layout.STATE_DTYPE).reshape(-1)
+    assert (after["other_land_units"] <= before["other_land_units"]).all()
+    sea_b, sea_a = before["other_sea_units"].astype(np.int32), after["other_sea_units"].astype(np.int32)
+    assert (sea_a[..., :12] <= sea_b[..., :12]).all()  # every defending type but the two battleship states
+    assert (sea_a[..., 12:].sum(axis=-1) <= sea_b[..., 12:].sum(axis=-1)).all()  # a hit battleship turns into a damaged one
+    # attackers may retreat to a neighbouring land, so only their total over the map is monotone
+    assert (after["land_state"]["infantry"].astype(np.int32).sum(axis=(-1, -2)) <=
+            before["land_state"]["infantry"].astype(np.int32).sum(axis=(-1, -2))).all()
+
+
 def test_expansion_golden(eng):
     g = np.load(os.path.join(GOLD, "expansion.npz"))
     n_actions, actions, children, status = eng.expand(g["leaves"])

@@ -73,3 +73,30 @@ def test_root_statistics_allreduce_two_ranks(tmp_path):
     assert np.array_equal(got["v"], want_v)
     assert np.allclose(got["x"], want_x, rtol=0, atol=1e-9)
     assert got["best"] == [6, 5, 4, 3, 2, 0][int(np.argmax(want_x))]
+
+
+def _shard_main(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    per, steps = 1000, 3
+    mine = torch.tensor([[root_parallel.shard_first_game_id(rank, world, k, per), per] for k in range(steps)], dtype=torch.int64)
+    gathered = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    # the job-wide playout count is the only reduction the sharded benchmark needs (bench.py sums plies the same way)
+    total = torch.tensor([per * steps], dtype=torch.int64)
+    dist.all_reduce(total)
+    if rank == 0:
+        torch.save({"ranges": torch.stack(gathered), "total": int(total.item())}, out)
+    dist.destroy_process_group()
+
+
+def test_sharded_game_id_ranges_two_ranks(tmp_path):
+    """bench.py --gpus N shards game-id ranges over ranks with no data-path collective: the ranges of 2 ranks x 3 steps
+    are disjoint and tile [0, 2 * 3 * 1000) exactly."""
+    out = str(tmp_path / "s.pt")
+    mp.spawn(_shard_main, args=(2, 29519, out), nprocs=2, join=True)
+    got = torch.load(out, weights_only=False)
+    r = got["ranges"].reshape(-1, 2).numpy()
+    r = r[np.argsort(r[:, 0])]
+    assert r[0, 0] == 0 and (r[1:, 0] == r[:-1, 0] + r[:-1, 1]).all()
+    assert r[-1, 0] + r[-1, 1] == got["total"] == 6000
