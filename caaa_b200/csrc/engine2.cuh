@@ -669,17 +669,23 @@ CAAA_HD_NOINLINE int stage_transport_units(Game* g, const RunCtx cx, unsigned mi
 }
 
 // ---- phases 3,4,5,12: move_land_unit_type, 1986-2060 ----
+// Walks the land-unit phases ph_first..ph_last of the pipeline in ONE flat loop (3..5 = tanks, artillery, infantry are
+// consecutive in the reference's turn, src/engine.cpp:4217-4219; 12 = AA guns): a lane whose game only has infantry to
+// move and a lane that is still moving tanks execute the same decision step together, and a game needs one visit
+// instead of up to three.  Per game the order of cells, lists and draws is exactly that of the separate phases; the
+// end-of-phase bookkeeping runs when a lane's cursor leaves a phase's cells.
 template <bool EXPAND>
-CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min, int ut, int ph, int yield = 0) {
-  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & W(ph)) != 0);
-  if (!(g->work & W(ph))) return PH_DONE;
+CAAA_HD_NOINLINE int move_land_units(Game* g, const RunCtx cx, unsigned min, int ph_first, int ph_last, int yield = 0) {
+  const uint32_t range = ((2u << ph_last) - 1u) & ~((1u << ph_first) - 1u);
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & range) != 0);
+  if (!(g->work & range)) return PH_DONE;
   const CaaaTables& t = CAAA_TAB(cx)->t;
   const int cur = g->cur;
-  const int mm = max_move_land(ut);
-  const int sc_first = ut == TANKS ? (int)SC_TANKS : ut == ARTILLERY ? (int)SC_ARTILLERY : ut == INFANTRY ? (int)SC_INFANTRY : (int)SC_AA_GUNS;
   bool processed = false, fresh = true;
-  int cell = 0;  // src * mm + (mm - moves)
-  if (g->cur_phase == ph) {
+  int ph = ph_first;
+  int cell = 0;  // within the phase: src * max_move + (max_move - moves)
+  if (g->cur_phase >= ph_first && g->cur_phase <= ph_last) {
+    ph = g->cur_phase;
     cell = g->cur_cell;
     fresh = g->cur_flags & CF_FRESH;
     processed = (g->cur_flags & CF_PROCESSED) != 0;
@@ -691,12 +697,26 @@ CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min,
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
     if (!active) continue;
-    const uint32_t cc = scan_cells(g, CAAA_TAB(cx)->scan + sc_first, NL * mm, cell, fresh);
+    const int ut = ph == CAAA_PH_MOVE_TANKS ? (int)TANKS : ph == CAAA_PH_MOVE_ARTILLERY ? (int)ARTILLERY : ph == CAAA_PH_MOVE_INFANTRY ? (int)INFANTRY : (int)AA_GUNS;
+    const int sc_first = ph == CAAA_PH_MOVE_TANKS ? (int)SC_TANKS : ph == CAAA_PH_MOVE_ARTILLERY ? (int)SC_ARTILLERY : ph == CAAA_PH_MOVE_INFANTRY ? (int)SC_INFANTRY : (int)SC_AA_GUNS;
+    const int n_cells = ph == CAAA_PH_MOVE_TANKS ? 2 * NL : NL;
+    const bool has_phase = (g->work & W(ph)) != 0;
+    uint32_t cc = 0;
+    if (has_phase) cc = scan_cells(g, CAAA_TAB(cx)->scan + sc_first, n_cells, cell, fresh);
+    else cell = n_cells;
     uint8_t* const arr = cell_arr(g, cc);
     const int src = cell_loc(cc), moves = cell_state(cc);
     converge<!EXPAND>(mact);
-    if (cell >= NL * mm) {
-      active = false;
+    if (cell >= n_cells) {  // this phase is done for this game: its end-of-phase bookkeeping, then the next phase's cells
+      if (has_phase) {
+        if (processed) clear_move_history(g);
+        g->work &= ~W(ph);
+      }
+      processed = false;
+      fresh = true;
+      cell = 0;
+      if (ph == ph_last) active = false;
+      else ph++;
       continue;
     }
     if (fresh) {
@@ -754,9 +774,13 @@ CAAA_HD_NOINLINE int move_land_unit_type(Game* g, const RunCtx cx, unsigned min,
     return PH_YIELDED;
   }
   g->cur_phase = CUR_NONE;
-  if (processed) clear_move_history(g);
-  g->work &= ~W(ph);
   return PH_DONE;
+}
+// one land-unit phase (reference move_land_unit_type, src/engine.cpp:1986-2060)
+template <bool EXPAND>
+CAAA_HD int move_land_unit_type(Game* g, const RunCtx cx, unsigned min, int ut, int ph, int yield = 0) {
+  (void)ut;
+  return move_land_units<EXPAND>(g, cx, min, ph, ph, yield);
 }
 
 // ---- phase 6: move_transport_units, 2062-2159 ----

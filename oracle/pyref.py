@@ -252,6 +252,15 @@ class HostSim(_Engine):
         return st
 
 
+    def rollout_many_merged(self, state, first_game_id, n, budget):
+        """Playouts with the three consecutive land-unit phases run as one merged visit (budget = yield granularity, 0 = none)."""
+        st = np.zeros(n, dtype=STATS_DTYPE)
+        buf = np.ascontiguousarray(state).view(np.uint8).reshape(-1)
+        self.lib.caaa_hostsim_rollout_many_merged(buf.ctypes.data_as(C.c_void_p), C.c_int64(first_game_id), C.c_int(n), C.c_int(budget),
+                                                  st.ctypes.data_as(C.c_void_p))
+        return st
+
+
 def have_ref():
     return os.path.exists(Ref.PATH)
 

@@ -173,6 +173,32 @@ extern "C" void caaa_hostsim_rollout_many_sliced(const void* s, int64_t first, i
     fill_stats(g, score, st + i);
   }
 }
+// like rollout_many_sliced, but tanks / artillery / infantry move in one merged visit (move_land_units over phases
+// 3..5), the way the phase-regrouped kernel runs them
+extern "C" void caaa_hostsim_rollout_many_merged(const void* s, int64_t first, int n, int budget, CaaaRolloutStats* st) {
+  for (int i = 0; i < n; i++) {
+    Game* g = &g_game;
+    import_state(g, (const uint8_t*)s);
+    begin_playout(g, g_cx, (uint64_t)first + (uint64_t)i);
+    double score = evaluate_state(g, g_cx);
+    while (score > 0.01 && score < 0.99 && g->turns < 1000) {
+      for (int ph = 0; ph < CAAA_PH_COUNT; ph++) {
+        if (ph == CAAA_PH_MOVE_TANKS) {
+          while (move_land_units<false>(g, g_cx, 0xffffffffu, CAAA_PH_MOVE_TANKS, CAAA_PH_MOVE_INFANTRY, budget) == PH_YIELDED) {
+          }
+          ph = CAAA_PH_MOVE_INFANTRY;
+          continue;
+        }
+        while (run_phase<false>(g, g_cx, ph, 0xffffffffu, budget) == PH_YIELDED) {
+        }
+      }
+      g->turns++;
+      score = evaluate_state(g, g_cx);
+    }
+    if (g->player % 2 == 1) score = 1 - score;
+    fill_stats(g, score, st + i);
+  }
+}
 extern "C" void caaa_hostsim_rollout_many_routed(const void* s, int64_t first, int n, CaaaRolloutStats* st) {
   caaa_hostsim_rollout_many_sliced(s, first, n, 1, st);
 }

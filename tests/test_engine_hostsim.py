@@ -104,3 +104,16 @@ def test_phases_resume_from_their_saved_cursor(port, hostsim):
     snaps = snapshots(port, 12)
     for i, st in enumerate(snaps[::3]):
         assert np.array_equal(port.rollout_many(st, 5000 + 10 * i, 2), hostsim.rollout_many_sliced(st, 5000 + 10 * i, 2, 1)), i
+
+
+def test_merged_land_phases_bit_exact(port, hostsim):
+    """Tanks, artillery and infantry moved in one merged flat loop (what the phase-regrouped kernel does) play exactly
+    the same game as the three separate phases, with and without yielding."""
+    s = pyref.start_state()
+    port.set_stream(1, SEED)
+    hostsim.set_stream(1, SEED)
+    want = port.rollout_many(s, 0, 400)
+    for budget in (0, 1, 3):
+        assert np.array_equal(want, hostsim.rollout_many_merged(s, 0, 400, budget)), budget
+    for i, st in enumerate(snapshots(port, 12)[::3]):
+        assert np.array_equal(port.rollout_many(st, 7000 + 10 * i, 2), hostsim.rollout_many_merged(st, 7000 + 10 * i, 2, 2)), i
