@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) advance_kernel(const DevTables*
 }
 
 // Isolated combat resolution (BASELINE config 3).
-__global__ void __launch_bounds__(SMALL_THREADS) battle_kernel(const DevTables* tables, const uint8_t* states, int n,
+__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) battle_kernel(const DevTables* tables, const uint8_t* states, int n,
                                                                unsigned long long seed, unsigned long long first_game_id,
                                                                uint8_t* out_states, int32_t* out_draws, CaaaBatchSummary* summary) {
   const DevTables* T = stage_tables(tables);
@@ -569,7 +569,7 @@ int caaa_gpu_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   CUDA_TRY(cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
-  CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
+  CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   CUDA_TRY(cudaFuncSetAttribute(actions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
@@ -712,8 +712,8 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
   CUDA_TRY(cudaMemcpyAsync(c.d_in, states, bytes, cudaMemcpyHostToDevice, c.stream));
   CUDA_TRY(cudaMemsetAsync(c.d_summary, 0, sizeof(CaaaBatchSummary), c.stream));
   CUDA_TRY(cudaEventRecord(c.ev0, c.stream));
-  const int grid = (n + SMALL_THREADS - 1) / SMALL_THREADS;
-  battle_kernel<<<grid, SMALL_THREADS, small_smem(), c.stream>>>(c.d_tables, (const uint8_t*)c.d_in, n, seed, first_game_id,
+  const int grid = (n + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;  // 7 warps per SM: the sweep is bound by per-warp latency
+  battle_kernel<<<grid, ROLLOUT_THREADS, rollout_smem(), c.stream>>>(c.d_tables, (const uint8_t*)c.d_in, n, seed, first_game_id,
                                                                  (uint8_t*)c.d_out, (int32_t*)c.d_aux2, c.d_summary);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c.ev1, c.stream));
