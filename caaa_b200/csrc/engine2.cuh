@@ -1035,6 +1035,121 @@ CAAA_HD_NOINLINE int move_destroyers_battleships(Game* g, const RunCtx cx, unsig
   return PH_DONE;
 }
 
+// Walks the three consecutive sea-mover phases 6..8 (loaded transports, submarines, surface ships; reference
+// src/engine.cpp:4220-4222) in ONE flat loop, like move_land_units does for the land movers: per game the cells, lists
+// and draws come in exactly the order of the separate phases (move_transport_units / move_subs /
+// move_destroyers_battleships above), but lanes that are in different phases share every decision step and a game
+// needs one visit instead of up to three.
+template <bool EXPAND>
+CAAA_HD_NOINLINE int move_sea_units(Game* g, const RunCtx cx, unsigned min, int yield = 0) {
+  constexpr uint32_t range = W(CAAA_PH_MOVE_TRANSPORTS) | W(CAAA_PH_MOVE_SUBS) | W(CAAA_PH_MOVE_SHIPS);
+  const unsigned m = vote_ballot<!EXPAND>(min, (g->work & range) != 0);
+  if (!(g->work & range)) return PH_DONE;
+  const int cur = g->cur;
+  bool processed = false, fresh = true;
+  int ph = CAAA_PH_MOVE_TRANSPORTS, cell = 0;
+  if (g->cur_phase >= CAAA_PH_MOVE_TRANSPORTS && g->cur_phase <= CAAA_PH_MOVE_SHIPS) {
+    ph = g->cur_phase;
+    cell = g->cur_cell;
+    fresh = g->cur_flags & CF_FRESH;
+    processed = (g->cur_flags & CF_PROCESSED) != 0;
+  } else if (g->work & W(CAAA_PH_MOVE_TRANSPORTS)) {
+#pragma unroll 1
+    for (int s = 0; s < NS; s++) {  // skip_empty_transports 2062-2075
+      uint8_t* e = su_ptr(g, s, TRANS_EMPTY);
+      const uint32_t n = e[1] + e[2] + e[3];
+      if (n) {
+        e[0] = (uint8_t)(e[0] + n);
+        e[1] = e[2] = e[3] = 0;
+      }
+    }
+  }
+  bool active = true, stop = false;
+  int steps = 0;
+  for (;;) {
+    const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
+    if (mact == 0) break;
+    if (should_yield<!EXPAND>(m, active, yield, steps)) break;
+    if (!active) continue;
+    const bool transports = ph == CAAA_PH_MOVE_TRANSPORTS, subs = ph == CAAA_PH_MOVE_SUBS;
+    const int sc_first = transports ? (int)SC_TRANSPORTS : subs ? (int)SC_SUBS : (int)SC_SHIPS;
+    const int n_cells = transports ? (int)SC_TRANSPORTS_N : subs ? (int)SC_SUBS_N : (int)SC_SHIPS_N;
+    const bool has_phase = (g->work & W(ph)) != 0;
+    uint32_t cc = 0;
+    if (has_phase) cc = scan_cells(g, CAAA_TAB(cx)->scan + sc_first, n_cells, cell, fresh);
+    else cell = n_cells;
+    uint8_t* const arr = cell_arr(g, cc);
+    const int ut = cell_type(cc), s = cell_loc(cc), st = cell_state(cc);
+    converge<!EXPAND>(mact);
+    if (cell >= n_cells) {  // this phase is done for this game
+      if (has_phase) {
+        if (processed) clear_move_history(g);
+        g->work &= ~W(ph);
+      }
+      processed = false;
+      fresh = true;
+      cell = 0;
+      if (ph == CAAA_PH_MOVE_SHIPS) active = false;
+      else ph++;
+      continue;
+    }
+    const uint32_t sa = (uint32_t)(s + NL);
+    if (fresh) {
+      fresh = false;
+      processed = true;
+      g->vm[0] = (uint8_t)sa;
+      g->nvm = 1;
+      add_valid_sea_moves(g, cx, s, transports ? st - 1 : 2, subs ? 16u : 0u);
+    }
+    uint32_t da = g->vm[0];
+    if (g->nvm > 1) {
+      if (g->answers_remaining == 0) {
+        stop = true;
+        active = false;
+        continue;
+      }
+      da = ai_input<EXPAND>(g, cx);
+    }
+    const int ds = (int)da - NL;
+    if (transports) {
+      if (g->blockade[ds] > 0) flag_combat(g, da, 2);
+      g->work |= W(CAAA_PH_UNLOAD_TRANSPORTS);
+    } else if (subs) {
+      if (g->enemy_count[ds] > 0) flag_combat(g, ds, 2);  // 2188,2194: sea index used as an air index
+    } else {
+      if (g->enemy_count[da] > 0) flag_combat(g, da, 2);
+    }
+    const int to = transports ? 1 : subs ? 0 : (int)done_moving_sea(ut);  // the state a moved (or staying) unit ends in
+    if (sa == da) {
+      arr[to] = (uint8_t)(arr[to] + arr[st]);
+      arr[st] = 0;
+      continue;
+    }
+    su_ptr(g, ds, ut)[to]++;
+    uts(g, cur, ds)[ut]++;
+    g->tot_sea[cur][ds]++;
+    arr[st]--;
+    uts(g, cur, s)[ut]--;
+    g->tot_sea[cur][s]--;
+    if (transports && ut <= TRANS_1T) {
+      g->small_cargo[ds]++;
+      g->small_cargo[s]--;
+      if (ut <= TRANS_1I) {
+        g->large_cargo[ds]++;
+        g->large_cargo[s]--;
+      }
+    }
+    if (ut == CARRIERS) carry_allied_fighters(g, cx, s, ds);
+  }
+  if (stop) return PH_STOPPED;
+  if (active) {
+    save_cursor(g, ph, cell, (fresh ? CF_FRESH : 0u) | (processed ? CF_PROCESSED : 0u), 0u, 0u);
+    return PH_YIELDED;
+  }
+  g->cur_phase = CUR_NONE;
+  return PH_DONE;
+}
+
 // ---- casualty removal ----
 // Take `hits` off a uint8 counter the way every reference casualty loop does: returns true when the
 // hits are used up (the reference then returns), false when the counter was wiped and hits remain.

@@ -193,6 +193,7 @@ void build_dev_tables(DevTables* out) {
     for (int st = 1; st <= 3; st++)
       for (int a = 0; a < NA; a++)
         t[SC_LAND_FIGHTERS + (st - 1) * NA + a] = pack(a < NL ? land_cell(a, FIGHTERS, st) : sea_cell(a - NL, FIGHTERS, st), FIGHTERS, a, st);
+    for (int sea = 0; sea < NS; sea++) t[SC_SUBS + sea] = pack(sea_cell(sea, SUBMARINES, 2), SUBMARINES, sea, 2);
     for (int c1 = 0; c1 < 5; c1++)
       for (int a = 0; a < NA; a++) {
         const int st = a < NL ? c1 + 1 : c1;

@@ -94,7 +94,8 @@ enum : int {
   SC_UNLOAD = SC_SHIPS + SC_SHIPS_N, SC_UNLOAD_N = 18,
   SC_LAND_FIGHTERS = SC_UNLOAD + SC_UNLOAD_N, SC_LAND_FIGHTERS_N = 24,
   SC_LAND_BOMBERS = SC_LAND_FIGHTERS + SC_LAND_FIGHTERS_N, SC_LAND_BOMBERS_N = 40,
-  SCAN_TOTAL = SC_LAND_BOMBERS + SC_LAND_BOMBERS_N
+  SC_SUBS = SC_LAND_BOMBERS + SC_LAND_BOMBERS_N, SC_SUBS_N = 3,
+  SCAN_TOTAL = SC_SUBS + SC_SUBS_N
 };
 
 // Read-only tables staged once per CTA in shared memory: the reference's topology tables plus

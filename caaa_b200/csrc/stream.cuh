@@ -323,9 +323,8 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
           // tanks, artillery and infantry are consecutive phases of one mover: one visit, one merged flat loop
           // (queues 4 and 5 stay empty)
           case CAAA_PH_MOVE_TANKS: res = move_land_units<false>(g, cx, mhave, CAAA_PH_MOVE_TANKS, CAAA_PH_MOVE_INFANTRY, yield); break;
-          case CAAA_PH_MOVE_TRANSPORTS: res = move_transport_units<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_MOVE_SUBS: res = move_subs<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_MOVE_SHIPS: res = move_destroyers_battleships<false>(g, cx, mhave, yield); break;
+          // ... and so are loaded transports, submarines and surface ships (queues 7 and 8 stay empty)
+          case CAAA_PH_MOVE_TRANSPORTS: res = move_sea_units<false>(g, cx, mhave, yield); break;
           case CAAA_PH_SEA_BATTLES: res = resolve_sea_battles<false>(g, cx, mhave, yield); break;
           case CAAA_PH_UNLOAD_TRANSPORTS: res = unload_transports<false>(g, cx, mhave, yield); break;
           case CAAA_PH_LAND_BATTLES: res = resolve_land_battles<false>(g, cx, mhave, yield); break;
@@ -370,9 +369,11 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         nxt = kind;
       } else if (runs && live) {
         uint32_t w = g->work & W_ALL_MOVES;
-        if (kind < Q_EOT) w &= ~((2u << (kind == CAAA_PH_MOVE_TANKS ? (int)CAAA_PH_MOVE_INFANTRY : kind)) - 1u);  // (after the end of
-        nxt = w ? __ffs(w) - 1 : Q_EOT;                                  // a turn or a fresh start every phase is open again)
+        const int last = kind == CAAA_PH_MOVE_TANKS ? (int)CAAA_PH_MOVE_INFANTRY : kind == CAAA_PH_MOVE_TRANSPORTS ? (int)CAAA_PH_MOVE_SHIPS : kind;
+        if (kind < Q_EOT) w &= ~((2u << last) - 1u);  // (after the end of a turn or a fresh start every phase is open again)
+        nxt = w ? __ffs(w) - 1 : Q_EOT;
         if (nxt == CAAA_PH_MOVE_ARTILLERY || nxt == CAAA_PH_MOVE_INFANTRY) nxt = CAAA_PH_MOVE_TANKS;  // the merged land mover
+        if (nxt == CAAA_PH_MOVE_SUBS || nxt == CAAA_PH_MOVE_SHIPS) nxt = CAAA_PH_MOVE_TRANSPORTS;      // the merged sea mover
       }
       const bool keep = false;  // (a warp never holds on to a game: every phase is a hop through the pool)
       unsigned mout = __ballot_sync(FULL, nxt >= 0 && !keep);

@@ -173,8 +173,8 @@ extern "C" void caaa_hostsim_rollout_many_sliced(const void* s, int64_t first, i
     fill_stats(g, score, st + i);
   }
 }
-// like rollout_many_sliced, but tanks / artillery / infantry move in one merged visit (move_land_units over phases
-// 3..5), the way the phase-regrouped kernel runs them
+// like rollout_many_sliced, but tanks / artillery / infantry (phases 3..5, move_land_units) and transports / subs / ships
+// (phases 6..8, move_sea_units) each move in one merged visit, the way the phase-regrouped kernel runs them
 extern "C" void caaa_hostsim_rollout_many_merged(const void* s, int64_t first, int n, int budget, CaaaRolloutStats* st) {
   for (int i = 0; i < n; i++) {
     Game* g = &g_game;
@@ -187,6 +187,12 @@ extern "C" void caaa_hostsim_rollout_many_merged(const void* s, int64_t first, i
           while (move_land_units<false>(g, g_cx, 0xffffffffu, CAAA_PH_MOVE_TANKS, CAAA_PH_MOVE_INFANTRY, budget) == PH_YIELDED) {
           }
           ph = CAAA_PH_MOVE_INFANTRY;
+          continue;
+        }
+        if (ph == CAAA_PH_MOVE_TRANSPORTS) {
+          while (move_sea_units<false>(g, g_cx, 0xffffffffu, budget) == PH_YIELDED) {
+          }
+          ph = CAAA_PH_MOVE_SHIPS;
           continue;
         }
         while (run_phase<false>(g, g_cx, ph, 0xffffffffu, budget) == PH_YIELDED) {
