@@ -4,21 +4,24 @@
 //
 // Why: in a player-turn only 10-45 % of the games have anything to do in a given phase, and the amount of
 // work per game is heavy-tailed, so a warp that walks the pipeline with the same 32 games issues most of its
-// instructions for 2-4 active lanes.  Here the games are REGROUPED BY PHASE inside every SM:
-//   * every CTA (one per SM) owns a private pool of POOL_MULT x 224 games in global memory (924 B each;
-//     the whole pool is ~90 MB and stays L2-resident) and steps them until the batch's ticket counter runs out;
-//   * per pipeline phase (0..14, 15 = the end-of-turn item: purchase, bookkeeping, rotation, scoring, finish +
-//     restart, 16 = free pool entries) the CTA keeps a bitmap of the pool entries waiting for that phase, in
-//     shared memory;
-//   * a warp claims up to 32 entries that all wait for the SAME phase (atomicAnd on the bitmap words), copies
-//     them into its 32 shared-memory slots with cp.async (all lanes move one game at a time: coalesced, fully
-//     pipelined), runs the phase with all lanes in lockstep (engine2.cuh), copies every game back and sets its
-//     bit in the bitmap of the next phase that has work for it (per-game work mask);
-//   * the warps of a CTA prefer the CTA's current phase, so they share its few KB of instructions in the SM's
-//     instruction caches; when that bitmap runs low they move to the fullest one.
+// instructions for 2-4 active lanes.  Here the games are REGROUPED BY PHASE:
+//   * the CTAs (one per SM, persistent) form groups of 16; every group owns a pool of 2 x 224 games per CTA in
+//     global memory (932 B each; 62 MB in total, L2-resident) and steps them until the batch's ticket counter
+//     runs out;
+//   * per kind of work (pipeline phases 0..14 -- with tanks/artillery/infantry and transports/subs/ships merged
+//     into one visit each --, 15 = the end-of-turn item: purchase, bookkeeping, rotation, scoring, finish +
+//     restart, 16 = free pool entries) the group keeps a bitmap of the pool entries waiting for it;
+//   * a warp claims up to LANES entries that all wait for the SAME kind (atomicAnd on bitmap words), copies them
+//     into its shared-memory slots (all 32 lanes move one game at a time: coalesced L2 loads, 4 games in
+//     flight), runs the phase on them in lockstep (engine2.cuh), copies every game back and sets its bit in the
+//     bitmap of the next phase that has work for it (per-game work mask);
+//   * the warps of a CTA serve the CTA's current kind while enough entries wait for it, so they share its few KB
+//     of instructions in the SM's instruction caches; then they move to the kind with the most entries per
+//     serving CTA.  Sixteen SMs pooling their games is what makes one kind's queue long enough for that.
 // No lane waits for a game of another phase, a game is only queued for phases in which it has something to
 // do, and finished pool entries restart from the ticket counter, which absorbs the long tail of game lengths.
-// Nothing is shared between SMs except the ticket counter, so there is no device-wide queue contention.
+// The only device-wide shared word is the ticket counter; queues are per group, so claims do not contend GPU-wide
+// (a single set of device-wide queues was measured: 92 % of the time went into claim contention).
 #pragma once
 
 namespace caaa {
@@ -133,11 +136,10 @@ __device__ __noinline__ void restart_lanes(const RolloutArgs& a, Game* warp_game
   }
 }
 
-// LANES = games per warp.  A warp serves ONE phase at a time: it claims games waiting for that phase, runs the
-// phase on them in lockstep, and -- because the work per game is heavy-tailed -- lets the phase YIELD as soon as a
-// quarter of its lanes are done: the finished games are routed on, their lanes are refilled with other games
-// waiting for the same phase, and the unfinished games simply resume from the cursor saved in the game
-// (engine2.cuh), without leaving shared memory.
+// LANES = games per warp (16: 14 warps per SM).  A warp serves ONE kind of work at a time: it claims games waiting
+// for it, runs the phase on them in lockstep and routes them on.  Optionally (yield_lanes / yield_battles, off by
+// default: measured neutral) a phase yields once a share of its batch is done; the stragglers keep their loop cursor
+// in the game (engine2.cuh), are queued for the same phase again and meet other stragglers there.
 template <bool STATS, int LANES>
 __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_stream(const RolloutArgs a, uint32_t* pool_all, int pool_mult,
                                                                                        GroupState* groups, int group_size, StreamDbg* dbg) {
@@ -255,14 +257,10 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
     }
     bool have = false;   // this lane holds a game of phase `kind`
     unsigned idx = 0;    // its pool entry
-    bool first = true;
-    const bool chaining = false;
-    for (;;) {  // ---- serve `kind`: fill the free lanes, run, route the finished games ----
-      const unsigned mhave0 = __ballot_sync(FULL, have);
-      const unsigned free_lanes = ~mhave0 & LANE_MASK;
-      int n_new = (free_lanes && !chaining) ? claim(kind, __popc(free_lanes)) : 0;
-      if (first && n_new == 0) break;
-      first = false;
+    {  // ---- serve `kind`: claim a batch, run it, route the games on ----
+      const unsigned free_lanes = LANE_MASK;
+      const int n_new = claim(kind, LANES);
+      if (n_new == 0) continue;
       CAAA_LAP(0);  // idle + select + claim
       if (n_new > 0) {
         last_work = clock64();
@@ -304,9 +302,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       }
       const bool runs = have;
       const unsigned mhave = __ballot_sync(FULL, runs);
-      if (mhave == 0) break;
-      // ---- run the phase on all held games in lockstep; it may yield when a quarter of the lanes are done and
-      // replacements are waiting ----
+      // ---- run the phase on all held games in lockstep ----
       // yield_pct > 0: the phase yields once that share of the batch is done; the stragglers are queued for the same
       // phase again (cursor saved in the game) and meet other stragglers there.  yield_battles_pct applies to the two
       // battle phases only, whose round counts have by far the longest tail.
@@ -375,8 +371,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         if (nxt == CAAA_PH_MOVE_ARTILLERY || nxt == CAAA_PH_MOVE_INFANTRY) nxt = CAAA_PH_MOVE_TANKS;  // the merged land mover
         if (nxt == CAAA_PH_MOVE_SUBS || nxt == CAAA_PH_MOVE_SHIPS) nxt = CAAA_PH_MOVE_TRANSPORTS;      // the merged sea mover
       }
-      const bool keep = false;  // (a warp never holds on to a game: every phase is a hop through the pool)
-      unsigned mout = __ballot_sync(FULL, nxt >= 0 && !keep);
+      unsigned mout = __ballot_sync(FULL, nxt >= 0);
       __syncwarp();
       while (mout) {
         const int j = __ffs(mout) - 1;
@@ -391,7 +386,6 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       __threadfence();
       __syncwarp();
       {
-        if (keep) nxt = -1;
         const unsigned peers = __match_any_sync(FULL, nxt);
         if (nxt >= 0) {
           atomicOr(&GS->bm[nxt][idx >> 5], 1u << (idx & 31u));
@@ -400,9 +394,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       }
       const unsigned nret = __popc(__ballot_sync(FULL, retired));
       if (lane == 0 && nret) atomicAdd(&GS->retired, (int)nret);
-      have = false;  // routed on, requeued, retired or finished: every lane is free again
       CAAA_LAP(4);  // copy out + publish
-      break;
     }
   }
 #undef CAAA_LAP
