@@ -499,6 +499,12 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
       std::fprintf(stderr, "stream dbg: batches %llu items/batch %.1f  idle+claim %.3f in %.3f compute %.3f restart %.3f out %.3f  Mcyc/warp %.1f\n",
                    h.batches, h.batches ? (double)h.items / (double)h.batches : 0.0, h.t[0] / tt, h.t[1] / tt, h.t[2] / tt, h.t[3] / tt,
                    h.t[4] / tt, tt / (grid * (STREAM_SLOTS / c.lanes)) / 1e6);
+      std::fprintf(stderr, "stream dbg: per kind  share of phase time / share of game visits:");
+      double kc = 0, ki = 0;
+      for (int q = 0; q < NQ; q++) { kc += (double)h.kind_cycles[q]; ki += (double)h.kind_items[q]; }
+      for (int q = 0; q < NQ; q++)
+        if (h.kind_items[q]) std::fprintf(stderr, "  k%d %.3f/%.3f", q, h.kind_cycles[q] / kc, h.kind_items[q] / ki);
+      std::fprintf(stderr, "\n");
     }
   } else if (c.sync_phases) {
     if (d_stats) rollout_kernel<true, true><<<grid, ROLLOUT_THREADS, rollout_smem(), stream>>>(a);

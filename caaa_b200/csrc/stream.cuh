@@ -85,6 +85,7 @@ __device__ __forceinline__ unsigned long long ld_vol_u64(const unsigned long lon
 
 struct StreamDbg {
   unsigned long long batches, items, t[6];
+  unsigned long long kind_cycles[NQ], kind_items[NQ];  // phase-code time and games per kind of work
 };
 
 // (Re)start the pool entries of the lanes with `need_start` from the batch's ticket counter: one fetch per warp,
@@ -352,6 +353,10 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         }
       }
       __syncwarp();
+      if (dbg != nullptr && lane == 0) {
+        atomicAdd(&dbg->kind_cycles[kind], (unsigned long long)(clock64() - d_c0));
+        atomicAdd(&dbg->kind_items[kind], (unsigned long long)n_new);
+      }
       CAAA_LAP(2);  // compute
       // ---- (re)start pool entries from the ticket counter (out of line: it runs once per playout, and the hot loop of
       // this kernel should stay small in the instruction cache) ----
