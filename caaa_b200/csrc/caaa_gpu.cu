@@ -56,6 +56,13 @@ struct RolloutArgs {
   int yield_lanes;   // a phase yields once this percentage of its batch is done; stragglers are requeued (0 = never)
   int scan_rounds;   // bitmap words / 32 a claim may look at
   int yield_battles; // like yield_lanes, for the two battle phases only
+  // SM-resident kernel (resident.cuh)
+  int yield_min;        // batches smaller than this never yield
+  int stick;            // bonus (in games) for the kind a warp served last
+  int min_batch;        // a warp waits up to min_batch_polls polls for a batch of at least this many games
+  int min_batch_polls;
+  unsigned idle_ns;     // sleep of an idle warp between two looks at the queues
+  int* abort_flag;      // set when the watchdog gave up (global memory, optional)
 };
 
 // Import every start / leaf state once: reference layout -> Game with all derived caches, ready to be
@@ -234,6 +241,8 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
 
 }  // namespace caaa
 #include "stream.cuh"
+#define CAAA_HAVE_STREAM_KERNEL 1
+#include "resident.cuh"
 namespace caaa {
 
 __device__ __forceinline__ void play_turn(Game* g, const RunCtx cx, unsigned m) {
@@ -381,7 +390,10 @@ struct Context {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long seed = 0, next_game_id = 0;
   bool sync_phases = false;  // CAAA_SYNC=1: CTA barrier after every phase (A/B knob)
-  bool streaming = true;     // CAAA_ROLLOUT_KERNEL=lockstep selects the walk-the-pipeline kernel instead
+  int kernel = 1;            // kernel of the most recent launch: 0 = SM-resident, 1 = phase-regrouped over a global pool, 2 = lockstep
+  int small_kernel = 2;      // the kernel for batches of up to small_batch playouts
+  int res_warps = 16;        // warps per CTA of the resident kernel (CAAA_WARPS)
+  int* d_abort = nullptr;    // watchdog flag of the resident kernel
   long long small_batch = 32768;  // batches up to this size go to the lockstep kernel (no pool hops: lower latency);
                                   // CAAA_ROLLOUT_KERNEL=stream sets it to 0
   int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
@@ -464,9 +476,77 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     a.scan_rounds = sr ? std::atoi(sr) : 4;
     if (a.scan_rounds < 1) a.scan_rounds = 1;
   }
+  auto env_int = [](const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+  };
+  a.yield_min = env_int("CAAA_YIELD_MIN", 4);
+  a.stick = env_int("CAAA_STICK", 0);
+  a.min_batch = env_int("CAAA_MIN_BATCH", 1);
+  a.min_batch_polls = env_int("CAAA_MIN_BATCH_POLLS", 8);
+  a.idle_ns = (unsigned)env_int("CAAA_IDLE_NS", 100);
+  a.abort_flag = c.d_abort;
+  {  // which kernel: CAAA_ROLLOUT_KERNEL = resident | stream | lockstep forces one; default = by batch size
+    const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
+    const long long small = env_int("CAAA_SMALL_BATCH", (int)c.small_batch);
+    if (rk != nullptr && std::strcmp(rk, "resident") == 0) c.kernel = 0;
+    else if (rk != nullptr && std::strcmp(rk, "stream") == 0) c.kernel = 1;
+    else if (rk != nullptr && std::strcmp(rk, "lockstep") == 0) c.kernel = 2;
+    else c.kernel = (long long)n_games > small ? 1 : c.small_kernel;
+  }
+  if (c.kernel == 0) {
+    // SM-resident kernel: spread small batches over all SMs (latency), fill every slot for large ones (regrouping)
+    const unsigned long long want32 = (n_games + 31) / 32;
+    const int grid_r = (int)(want32 < (unsigned long long)c.sm_count ? want32 : (unsigned long long)c.sm_count);
+    const unsigned long long per_cta = (n_games + grid_r - 1) / grid_r;
+    int n_slots = (int)((per_cta + 31) / 32 * 32);
+    if (n_slots > RES_SLOTS) n_slots = RES_SLOTS;
+    if (n_slots < 32) n_slots = 32;
+    ResDbg* d_dbg = nullptr;
+    if (std::getenv("CAAA_DEBUG") != nullptr) {
+      int rc2 = grow(&c.d_pool, &c.pool_cap, sizeof(ResDbg));
+      if (rc2 != CAAA_OK) return rc2;
+      d_dbg = (ResDbg*)c.d_pool;
+      CUDA_TRY(cudaMemsetAsync(d_dbg, 0, sizeof(ResDbg), stream));
+    }
+    CUDA_TRY(cudaMemsetAsync(c.d_abort, 0, sizeof(int), stream));
+    int res_warps = env_int("CAAA_WARPS", c.res_warps);
+    if (res_warps < 1) res_warps = 1;
+    if (res_warps > 32) res_warps = 32;
+    const int threads = res_warps * 32;
+    if (res_warps <= 16) {
+      if (d_stats) rollout_kernel_resident<true, 16><<<grid_r, threads, RES_SMEM, stream>>>(a, n_slots, d_dbg);
+      else rollout_kernel_resident<false, 16><<<grid_r, threads, RES_SMEM, stream>>>(a, n_slots, d_dbg);
+    } else if (res_warps <= 24) {
+      if (d_stats) rollout_kernel_resident<true, 24><<<grid_r, threads, RES_SMEM, stream>>>(a, n_slots, d_dbg);
+      else rollout_kernel_resident<false, 24><<<grid_r, threads, RES_SMEM, stream>>>(a, n_slots, d_dbg);
+    } else {
+      if (d_stats) rollout_kernel_resident<true, 32><<<grid_r, threads, RES_SMEM, stream>>>(a, n_slots, d_dbg);
+      else rollout_kernel_resident<false, 32><<<grid_r, threads, RES_SMEM, stream>>>(a, n_slots, d_dbg);
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (d_dbg != nullptr) {
+      ResDbg h;
+      cudaStreamSynchronize(stream);
+      cudaMemcpy(&h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      const double tt = (double)(h.t[0] + h.t[1] + h.t[2] + h.t[3]);
+      std::fprintf(stderr, "resident dbg: batches %llu games/batch %.2f  idle+claim %.3f phase %.3f restart %.3f route %.3f  Mcyc/warp %.1f\n",
+                   h.batches, h.batches ? (double)h.items / (double)h.batches : 0.0, h.t[0] / tt, h.t[1] / tt, h.t[2] / tt, h.t[3] / tt,
+                   tt / ((double)grid_r * res_warps) / 1e6);
+      double kc = 0, ki = 0;
+      for (int q = 0; q < NQ; q++) { kc += (double)h.kind_cycles[q]; ki += (double)h.kind_items[q]; }
+      std::fprintf(stderr, "resident dbg: per kind  time share / visit share / games per batch / kcyc per batch:");
+      for (int q = 0; q < NQ; q++)
+        if (h.kind_items[q])
+          std::fprintf(stderr, "  k%d %.3f/%.3f/%.1f/%.1f", q, h.kind_cycles[q] / kc, h.kind_items[q] / ki,
+                       (double)h.kind_items[q] / (double)h.kind_batches[q], h.kind_cycles[q] / 1e3 / (double)h.kind_batches[q]);
+      std::fprintf(stderr, "\n");
+    }
+    return CAAA_OK;
+  }
   const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
   const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
-  if (c.streaming && (long long)n_games > c.small_batch) {
+  if (c.kernel == 1) {
     const size_t need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game);
     const int n_groups = (grid + c.group_size - 1) / c.group_size;
     const size_t need16 = (need + 15) / 16 * 16;
@@ -544,14 +624,19 @@ int caaa_gpu_init(int device) {
   CUDA_TRY(cudaMemcpy(c.d_tables, &c.host_tables, sizeof(DevTables), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&c.d_ticket, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&c.d_summary, sizeof(CaaaBatchSummary)));
+  CUDA_TRY(cudaMalloc(&c.d_abort, sizeof(int)));
+  CUDA_TRY(cudaMemset(c.d_abort, 0, sizeof(int)));
   CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&c.ev0));
   CUDA_TRY(cudaEventCreate(&c.ev1));
   const char* sy = std::getenv("CAAA_SYNC");
   c.sync_phases = sy != nullptr && std::atoi(sy) != 0;
   const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
-  c.streaming = !(rk != nullptr && std::strcmp(rk, "lockstep") == 0);
-  if (rk != nullptr && std::strcmp(rk, "stream") == 0) c.small_batch = 0;
+  (void)rk;
+  const char* rw = std::getenv("CAAA_WARPS");
+  c.res_warps = rw ? std::atoi(rw) : 16;
+  if (c.res_warps < 1) c.res_warps = 1;
+  if (c.res_warps > 32) c.res_warps = 32;
   const char* pm = std::getenv("CAAA_POOL_MULT");
   c.pool_mult = pm ? std::atoi(pm) : 2;
   if (c.pool_mult < 1) c.pool_mult = 1;
@@ -569,6 +654,12 @@ int caaa_gpu_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
@@ -590,6 +681,7 @@ int caaa_gpu_shutdown(void) {
   cudaFree(c.d_tables);
   cudaFree(c.d_ticket);
   cudaFree(c.d_summary);
+  cudaFree(c.d_abort);
   if (c.d_in) cudaFree(c.d_in);
   if (c.d_out) cudaFree(c.d_out);
   if (c.d_aux) cudaFree(c.d_aux);
@@ -654,7 +746,12 @@ int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollou
   CaaaBatchSummary s;
   CUDA_TRY(cudaMemcpyAsync(&s, c.d_summary, sizeof(s), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
-  for (int gidx = 0; c.streaming && (long long)n_games > c.small_batch && gidx < c.n_groups_last; gidx++) {  // watchdog of the phase-regrouped kernel
+  if (c.kernel == 0) {
+    int aborted = 0;
+    CUDA_TRY(cudaMemcpy(&aborted, c.d_abort, sizeof(int), cudaMemcpyDeviceToHost));
+    if (aborted) return fail(CAAA_E_CUDA, "rollout kernel stopped by its watchdog: no claimable game although the batch was unfinished");
+  }
+  for (int gidx = 0; c.kernel == 1 && gidx < c.n_groups_last; gidx++) {  // watchdog of the phase-regrouped kernel
     int aborted = 0;
     CUDA_TRY(cudaMemcpy(&aborted, &c.d_groups_last[gidx].aborted, sizeof(int), cudaMemcpyDeviceToHost));
     if (aborted) return fail(CAAA_E_CUDA, "rollout kernel stopped by its watchdog: no claimable game although the batch was unfinished");

@@ -56,16 +56,21 @@ typedef struct CaaaUnitsSea {
   uint8_t bombers[5];
 } CaaaUnitsSea; /* 57 bytes */
 
-typedef struct CaaaGameState {
-  uint8_t player_index;
-  uint8_t money[CAAA_PLAYERS];
-  uint8_t builds_left[CAAA_AIRS];
-  CaaaLandState land_state[CAAA_LANDS];
-  CaaaUnitsSea units_sea[CAAA_SEAS];
-  uint8_t other_land_units[CAAA_PLAYERS - 1][CAAA_LANDS][CAAA_LAND_UNIT_TYPES];
-  uint8_t other_sea_units[CAAA_PLAYERS - 1][CAAA_SEAS][CAAA_SEA_UNIT_TYPES - 1];
-  uint8_t flagged_for_combat[CAAA_AIRS];
+/* the member list, shared with caaa_engine_compat.h (which must declare the same bytes under the
+ * reference's own type name so that its C++ symbols mangle like the reference's) */
+#define CAAA_GAME_STATE_MEMBERS                                                            \
+  uint8_t player_index;                                                                    \
+  uint8_t money[CAAA_PLAYERS];                                                             \
+  uint8_t builds_left[CAAA_AIRS];                                                          \
+  CaaaLandState land_state[CAAA_LANDS];                                                    \
+  CaaaUnitsSea units_sea[CAAA_SEAS];                                                       \
+  uint8_t other_land_units[CAAA_PLAYERS - 1][CAAA_LANDS][CAAA_LAND_UNIT_TYPES];            \
+  uint8_t other_sea_units[CAAA_PLAYERS - 1][CAAA_SEAS][CAAA_SEA_UNIT_TYPES - 1];           \
+  uint8_t flagged_for_combat[CAAA_AIRS];                                                   \
   uint8_t skipped_moves[CAAA_AIRS][CAAA_AIRS]; /* one byte per flag, bit 0 only */
+
+typedef struct CaaaGameState {
+  CAAA_GAME_STATE_MEMBERS
 } CaaaGameState; /* 670 bytes */
 
 #define CAAA_STATE_BYTES 670

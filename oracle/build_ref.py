@@ -154,6 +154,12 @@ def main():
             t = patch_engine(t)
         with open(os.path.join(SRC, tu), "w") as f:
             f.write(t)
+    # the reference's CLI driver, unpatched: tests/test_reference_links.py links it (with mcts.cpp and the data
+    # TUs above) against libcaaa_gpu.so to prove the drop-in boundary; it is not part of libcaaa_ref.so / ref_cli
+    shutil.copy(os.path.join(REF, "src", "main.cpp"), os.path.join(SRC, "main.cpp"))
+    os.chmod(os.path.join(SRC, "main.cpp"), 0o644)
+    shutil.copy(os.path.join(REF, "game_data.json"), os.path.join(OUT, "game_data.json"))
+    os.chmod(os.path.join(OUT, "game_data.json"), 0o644)
     p = os.path.join(INC, "land.h")
     os.chmod(p, 0o644)
     with open(p) as f:

@@ -92,12 +92,25 @@ static bool g_auto_game_id = true;        // game id = running playout counter
 static uint64_t g_playout_counter = 0;
 static uint32_t g_draws = 0;
 
+static uint32_t g_block[4];               // current 16-byte Philox block (one block serves 16 draws, as on the GPU)
+static uint32_t g_block_index = 0xffffffffu;
+static uint64_t g_block_game = 0, g_block_seed = 0;
+
 uint8_t caaa_ref_next_byte() {
   uint32_t d = g_draws++;
   if (g_stream_mode == 0) {
     return RANDOM_NUMBERS[random_number_index++];  // src/engine.cpp:1296,2562,2577 verbatim
   }
-  return caaa_philox_byte_ref(g_seed, g_game_id, d);
+  if ((d >> 4) != g_block_index || g_block_game != g_game_id || g_block_seed != g_seed) {
+    const uint32_t ctr[4] = {d >> 4, (uint32_t)g_game_id, (uint32_t)(g_game_id >> 32), 0u};
+    const uint32_t key[2] = {(uint32_t)g_seed, (uint32_t)(g_seed >> 32)};
+    caaa_philox4x32_10_ref(ctr, key, g_block);
+    g_block_index = d >> 4;
+    g_block_game = g_game_id;
+    g_block_seed = g_seed;
+  }
+  const uint32_t k = d & 15u;
+  return (uint8_t)(g_block[k >> 2] >> (8u * (k & 3u)));
 }
 
 uint16_t caaa_ref_begin_playout(uint16_t table_size) {

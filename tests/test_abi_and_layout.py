@@ -36,10 +36,10 @@ def test_header_symbols_exported():
         assert hasattr(lib, name), name
     # the reference-named C++ entry points of caaa_engine_compat.h (Itanium-mangled)
     for name in ("_Z20initialize_constantsv", "_Z14load_game_dataPKc", "_Z19get_game_state_copyv",
-                 "_Z11clone_stateP13CaaaGameState", "_Z10free_stateP13CaaaGameState",
-                 "_Z20get_possible_actionsP13CaaaGameStatePhPA20_h", "_Z12apply_actionP13CaaaGameStateh",
-                 "_Z17is_terminal_stateP13CaaaGameState", "_Z14evaluate_stateP13CaaaGameState",
-                 "_Z26random_play_until_terminalP13CaaaGameState"):
+                 "_Z11clone_stateP9GameState", "_Z10free_stateP9GameState",
+                 "_Z20get_possible_actionsP9GameStatePhPA20_h", "_Z12apply_actionP9GameStateh",
+                 "_Z17is_terminal_stateP9GameState", "_Z14evaluate_stateP9GameState",
+                 "_Z26random_play_until_terminalP9GameState"):
         assert hasattr(lib, name), name
 
 
