@@ -10,12 +10,18 @@ is sharded by game-id range with no data-path collective (weak scaling).  Rank 0
   value     playouts/s, states and results resident in HBM (device-pointer C-ABI entry point)
   e2e       same metric through the host-buffer C-ABI call (H2D of the states, D2H of the results inside)
   roofline  HBM roofline of the rollout kernel from algorithmic bytes (1340 B per ply)
-            and the live CUDA-event duration; the binding limit of this kernel is per-warp latency /
-            instruction issue, which is reported from ncu under profiles/
-  cpu_baseline  the reference's own CPU rollout loop (oracle/_ref) on ONE host core, bounded sample
+            and the live CUDA-event duration.  The BINDING limit of this kernel is instruction issue /
+            per-warp latency, so `roofline.issue` carries the issue-side counters (issue-slot utilisation,
+            active threads per issued instruction, thread instructions per ply) and `roofline.traffic` the
+            DRAM bytes per launch, both read from the committed ncu export profiles/r2_rollout_counters.json
+            (made by tools/ncu_extract.py from an `ncu --set full` capture of this same command)
+  cpu_baseline  the reference's own CPU rollout loop (oracle/_ref) on ONE host core, bounded sample, on
+            the reference's own glibc byte stream (mode 0) and on the Philox stream the GPU uses (mode 1)
 
 `--impl reference` times the reference's CPU loop on all host cores instead (one process per core: the
-reference engine keeps its state in file-scope globals and cannot be threaded).
+reference engine keeps its state in file-scope globals and cannot be threaded), on its own byte stream.
+With N > 1 the line also carries `config.root_parallel`: a short root-parallel MCTS (BASELINE config 5) whose
+root statistics are all-reduced by the C entry point caaa_root_allreduce and checked against the host-side sum.
 """
 import argparse
 import json
@@ -37,9 +43,16 @@ METRIC = "playouts/sec"
 # rollout_kernel_stream (the playouts)
 KERNELS_PER_BATCH = 3
 ROLLOUT_KERNEL = "rollout_kernel_stream<false, 16>"
-# dram__bytes_read.sum + dram__bytes_write.sum of one rollout_kernel_stream launch of 2**20 playouts
-# (profiles/dram_r1_pool2.csv, profiles/r1_ncu_summary.md); None when this run uses another batch size
-NCU_DRAM_BYTES_PER_1M_LAUNCH = 57_682_444_032  # 7.4 MB read + 57.7 GB written (profiles/dram_r1_pool2.csv)
+# counters of one rollout_kernel_stream launch of 2**20 playouts, exported from the ncu capture of this command
+NCU_COUNTERS = os.path.join(ROOT, "profiles", "r2_rollout_counters.json")
+
+
+def ncu_counters(playouts):
+    """Issue-side counters and DRAM traffic of the dominant kernel (None when absent or for another batch size)."""
+    if playouts != (1 << 20) or not os.path.exists(NCU_COUNTERS):
+        return None
+    with open(NCU_COUNTERS) as f:
+        return json.load(f)
 
 
 def measured_peaks():
@@ -130,13 +143,14 @@ def reference_arm(args):
         return 0
     cores = os.cpu_count() or 1
     per_proc = args.ref_playouts_per_core
+    mode = 0  # the reference's own byte stream (glibc table); the games differ from the GPU's, the rate is what is compared
     for _ in range(args.warmup):
-        run_ref_cli(cores, max(200, per_proc // 10), 1)
+        run_ref_cli(cores, max(200, per_proc // 10), mode)
     tot_playouts = tot_plies = 0
     tot_t = 0.0
     kind = "reference"
     for k in range(args.steps):
-        r = run_ref_cli(cores, per_proc, 1, first=k * cores * per_proc)
+        r = run_ref_cli(cores, per_proc, mode, first=k * cores * per_proc)
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_cli has not been built"}))
             return 0
@@ -152,7 +166,7 @@ def reference_arm(args):
                                "reference CPU loop random_play_until_terminal, one process per host core",
                    "playouts_per_step": cores * per_proc, "plies_per_sec": tot_plies / tot_t},
         "cpu_baseline": {"value": value, "unit": "playouts/s", "cores": cores, "kind": kind,
-                         "sample": f"{args.steps} x {cores} processes x {per_proc} playouts, Philox stream"},
+                         "sample": f"{args.steps} x {cores} processes x {per_proc} playouts, the reference's own byte stream"},
         "e2e": {"value": value, "unit": "playouts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -241,6 +255,17 @@ def ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * P * e2e_steps / float(e2e_s.item())
 
+    # ---- N > 1: BASELINE config 5 beside the headline: root-parallel MCTS, one tree per GPU, root statistics all-reduced by
+    # the library's NCCL entry point and checked against the host-side sum of the per-rank statistics ----
+    rp = None
+    if world > 1 and not args.no_root_parallel:
+        from caaa_b200 import host, root_parallel
+        comm = root_parallel.NcclRootComm(eng)
+        host.mcts_search(eng, s0, 256, 64, 256, 1)  # warm-up
+        rp = root_parallel.measured_root_parallel(eng, comm, s0, args.mcts_iterations, 4096, 256, 0xCAAA)
+        comm.close()
+        rp["note"] = ("one pipelined search per GPU (caaa_mcts_search: 256 leaves x 4096 rollouts per device batch, two batches in "
+                      "flight), seed = base + rank; exchange = caaa_root_allreduce_host (ncclAllReduce of <= 20 x {int64, double})")
     if rank == 0:
         peak, peak_src = measured_peaks()
         per_launch_ms = statistics.mean(step_ms)
@@ -248,12 +273,27 @@ def ours(args):
         achieved = plies_per_launch * BYTES_PER_PLY / (per_launch_ms * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = run_ref_cli(1, args.cpu_sample, 1)
-            if r is not None:
-                cpu = {"value": r[0] / r[2], "unit": "playouts/s", "cores": 1, "kind": "reference",
-                       "sample": f"{args.cpu_sample} playouts from the start position, one process, Philox stream "
-                                 f"({r[2]:.1f} s), oracle/_ref = the patched reference build",
-                       "plies_per_sec": r[1] / r[2]}
+            r0 = run_ref_cli(1, args.cpu_sample // 2, 0)  # the reference's own glibc table stream
+            r1 = run_ref_cli(1, args.cpu_sample // 2, 1)  # the Philox stream the GPU plays (same games as the GPU's)
+            if r0 is not None and r1 is not None:
+                cpu = {"value": r0[0] / r0[2], "unit": "playouts/s", "cores": 1, "kind": "reference",
+                       "sample": f"{args.cpu_sample // 2} playouts from the start position, one process, the reference's own "
+                                 f"byte stream ({r0[2]:.1f} s); oracle/_ref = the patched reference build",
+                       "plies_per_sec": r0[1] / r0[2], "plies_per_playout": r0[1] / r0[0],
+                       "philox_stream": {"value": r1[0] / r1[2], "plies_per_sec": r1[1] / r1[2], "plies_per_playout": r1[1] / r1[0],
+                                         "sample": f"{args.cpu_sample // 2} playouts, Philox4x32-10 stream ({r1[2]:.1f} s)"}}
+        nc = ncu_counters(P)
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": nc["dram_bytes_per_launch"] if nc else None, "peak_source": peak_src, "kernel": ROLLOUT_KERNEL,
+                    "note": "HBM view as the contract asks (algorithmic 1340 B/ply); this integer, branchy path is bound by "
+                            "instruction issue and per-warp latency, see `issue`"}
+        if nc:
+            # issue roofline: 148 SMs x 4 schedulers x 1 warp instruction per cycle; lanes: 32 threads per instruction
+            roofline["issue"] = {"warp_issue_frac": nc["warp_issue_frac"], "active_threads_per_inst": nc["active_threads_per_inst"],
+                                 "thread_issue_frac": nc["thread_issue_frac"], "thread_inst_per_ply": nc["thread_inst_per_ply"],
+                                 "warp_inst_per_ply": nc["warp_inst_per_ply"], "branch_uniformity_pct": nc["branch_uniformity_pct"],
+                                 "warps_active_pct": nc["warps_active_pct"], "source": "profiles/r2_rollout_counters.json "
+                                 "(ncu --set full of this command; tools/ncu_extract.py)"}
         line = {
             "metric": METRIC, "value": value, "unit": "playouts/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * total_s / args.steps, "higher_is_better": True,
@@ -264,16 +304,14 @@ def ours(args):
                        "plies_per_playout": plies_total / (world * P * args.steps), "flagged_playouts": float(flagged.item()),
                        "l2": "256 MiB write between timed steps (untimed); the 62 MB game pool is re-initialised by every step",
                        "sharding": "game-id ranges per rank, no data-path collective"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_DRAM_BYTES_PER_1M_LAUNCH if P == (1 << 20) else None, "peak_source": peak_src,
-                         "kernel": ROLLOUT_KERNEL,
-                         "note": "algorithmic 1340 B/ply; the kernel is bound by per-warp latency and lane occupancy, "
-                                 "not by HBM: see profiles/r1_ncu_summary.md"},
+            "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "playouts/s", "h2d_bytes_per_step": 670, "d2h_bytes_per_step": 8 * P + 56},
             "gpu_launches": launches, "clocks": clocks,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if rp is not None:
+            line["config"]["root_parallel"] = rp
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -290,6 +328,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=40000, help="playouts of the single-core CPU baseline")
     ap.add_argument("--ref-playouts-per-core", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-root-parallel", action="store_true")
+    ap.add_argument("--mcts-iterations", type=int, default=1024, help="leaves per GPU of the root-parallel block (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -13,7 +13,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
+#include <thread>
 
 #include "../../include/caaa_gpu.h"
 #include "engine2.cuh"
@@ -269,41 +274,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) advance_kernel(const DevTables*
   if (out_draws) out_draws[i] = (int32_t)g->draws;
 }
 
-// Isolated combat resolution (BASELINE config 3).
-__global__ void __launch_bounds__(ROLLOUT_THREADS, 1) battle_kernel(const DevTables* tables, const uint8_t* states, int n,
-                                                               unsigned long long seed, unsigned long long first_game_id,
-                                                               uint8_t* out_states, int32_t* out_draws, CaaaBatchSummary* summary) {
-  const DevTables* T = stage_tables(tables);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long draws = 0, flagged = 0, one = 0;
-  const unsigned m = __ballot_sync(FULL, i < n);
-  if (i < n) {
-    Game* g = my_game();
-    const RunCtx cx{T, (uint32_t)seed, (uint32_t)(seed >> 32)};
-    import_state(g, states + (size_t)i * CAAA_STATE_BYTES);
-    begin_playout(g, cx, first_game_id + (unsigned long long)i);
-    resolve_sea_battles<false>(g, cx, m);
-    resolve_land_battles<false>(g, cx, m);
-    if (out_states) export_state(g, out_states + (size_t)i * CAAA_STATE_BYTES);
-    if (out_draws) out_draws[i] = (int32_t)g->draws;
-    draws = g->draws;
-    flagged = g->status != 0;
-    one = 1;
-  }
-  if (summary != nullptr) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      draws += __shfl_down_sync(FULL, draws, o);
-      flagged += __shfl_down_sync(FULL, flagged, o);
-      one += __shfl_down_sync(FULL, one, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd((unsigned long long*)&summary->playouts, one);
-      atomicAdd((unsigned long long*)&summary->draws, draws);
-      atomicAdd((unsigned long long*)&summary->flagged, flagged);
-    }
-  }
-}
+}  // namespace caaa
+#include "battle.cuh"
+namespace caaa {
 
 // Stop-at-decision mode (reference get_possible_actions / apply_action, src/engine.cpp:4050-4183).
 __device__ __forceinline__ void run_until_decision(Game* g, const RunCtx cx) {
@@ -364,16 +337,106 @@ __global__ void __launch_bounds__(SMALL_THREADS) evaluate_kernel(const DevTables
   scores[i] = evaluate_state(g, cx);
 }
 
+// Leaf batches (MCTS): the child each visited leaf rolls out, chosen on the device so that the expansion's children
+// never leave it before the rollout (reference src/mcts.cpp:84-94: expand, `rand() % num_children`, rollout).
+// Terminal leaves and leaves without a playable child roll out from themselves (picked = -1).
+__global__ void pick_kernel(const uint8_t* leaves, int n, const double* scores, const uint8_t* n_actions, const uint32_t* status,
+                            const uint64_t* pick, const uint8_t* children, uint8_t* targets, int32_t* picked) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  __shared__ int s_src;
+  if (threadIdx.x == 0) {
+    const bool terminal = scores[i] > 0.99 || scores[i] < 0.01;  // reference src/engine.cpp:4244-4248
+    int k_sel = -1;
+    if (!terminal && !(status[i] & 0x80000000u)) {
+      int valid = 0;
+      for (int k = 0; k < n_actions[i]; k++) valid += !((status[i] >> k) & 1u);  // children whose apply_action returns
+      if (valid > 0) {
+        int r = (int)(pick[i] % (uint64_t)valid);
+        for (int k = 0; k < n_actions[i]; k++) {
+          if ((status[i] >> k) & 1u) continue;
+          if (r-- == 0) {
+            k_sel = k;
+            break;
+          }
+        }
+      }
+    }
+    picked[i] = k_sel;
+    s_src = k_sel;
+  }
+  __syncthreads();
+  const int k_sel = s_src;
+  const uint8_t* src = k_sel < 0 ? leaves + (size_t)i * CAAA_STATE_BYTES : children + ((size_t)i * CAAA_ACTIONS + k_sel) * CAAA_STATE_BYTES;
+  uint8_t* dst = targets + (size_t)i * CAAA_STATE_BYTES;
+  for (int b = threadIdx.x; b < CAAA_STATE_BYTES; b += blockDim.x) dst[b] = src[b];
+}
+
+// Per-leaf sum of the rollout results in a FIXED order (lane-strided partial sums, then a shuffle tree), so that a
+// search is reproducible: one warp per leaf, results[i * per_leaf .. (i + 1) * per_leaf).  Only n doubles go back to the
+// host (reference src/mcts.cpp:96-105 back-propagates one result at a time; the sum of a leaf's results is what its
+// path needs).
+__global__ void reduce_results_kernel(const double* results, int n, int per_leaf, double* sums) {
+  const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const double* r = results + (size_t)warp * per_leaf;
+  double acc = 0.0;
+  for (int j = lane; j < per_leaf; j += 32) acc += r[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULL, acc, o);
+  if (lane == 0) sums[warp] = acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side of the C-ABI
 // ------------------------------------------------------------------------------------------------
+constexpr size_t BATTLE_CHUNK = 131072;  // states per pipeline chunk (88 MB each way), a multiple of 32
+struct BattlePipe {  // pinned staging + streams of the host-buffer battle entry point
+  static constexpr int NBUF = 3;
+  bool ready = false;
+  void *h_in[NBUF] = {}, *h_out[NBUF] = {}, *d_in[NBUF] = {}, *d_out[NBUF] = {};
+  int32_t *h_draws[NBUF] = {}, *d_draws[NBUF] = {};
+  cudaStream_t stream[NBUF] = {};
+  cudaEvent_t k0[NBUF] = {}, k1[NBUF] = {}, done[NBUF] = {};
+};
+// Scratch of ONE rollout launch.  An asynchronous launch (caaa_gpu_rollout_batch_device) owns its slot until its
+// `done` event has fired; the next user of the slot waits for that event on the device, so launches issued on
+// different streams overlap safely (the drain of one batch then overlaps the start of the next).
+constexpr int N_LAUNCH_SLOTS = 3;
+struct LaunchSlot {
+  void* d_templates = nullptr;  // pre-imported start states + their first scores
+  size_t templates_cap = 0;
+  void* d_pool = nullptr;       // game pool + group state (+ debug counters) of the phase-regrouped kernel
+  size_t pool_cap = 0;
+  unsigned long long* d_ticket = nullptr;
+  int* d_abort = nullptr;       // set by a kernel's watchdog
+  cudaEvent_t done = nullptr;
+  bool used = false;
+};
+// One asynchronous MCTS leaf batch: pinned staging on the host, everything else resident on the device.
+constexpr int N_LEAF_BATCHES = 3;
+struct LeafBatch {
+  bool ready = false, in_flight = false;
+  int cap = 0, n = 0;            // leaves allocated / in this batch
+  size_t results_cap = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  uint8_t *h_in = nullptr, *h_out = nullptr;   // pinned: leaves + picks in; everything collect() returns out
+  uint8_t *d_in = nullptr, *d_out = nullptr;   // device mirrors of the two
+  uint8_t* d_children = nullptr;               // n x 20 x 670
+  uint8_t* d_targets = nullptr;                // n x 670: the states the rollouts start from
+  double* d_results = nullptr;                 // n x rollouts_per_leaf
+  CaaaBatchSummary* d_summary = nullptr;
+};
 struct Context {
   bool ready = false;
+  BattlePipe battle;
+  LeafBatch leaf[N_LEAF_BATCHES];
+  int rollout_sms = 0;  // SMs a rollout launch may occupy (0 = all): a search leaves a few free for the next batch's expansion
   int device = -1;
   int sm_count = 0;
   DevTables host_tables;
   DevTables* d_tables = nullptr;
-  unsigned long long* d_ticket = nullptr;
   CaaaBatchSummary* d_summary = nullptr;
   // growable scratch for the host-buffer entry points
   void* d_in = nullptr;
@@ -384,8 +447,6 @@ struct Context {
   size_t aux_cap = 0;
   void* d_aux2 = nullptr;
   size_t aux2_cap = 0;
-  void* d_templates = nullptr;  // pre-imported start states + their first scores
-  size_t templates_cap = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   unsigned long long seed = 0, next_game_id = 0;
@@ -393,16 +454,14 @@ struct Context {
   int kernel = 1;            // kernel of the most recent launch: 0 = SM-resident, 1 = phase-regrouped over a global pool, 2 = lockstep
   int small_kernel = 2;      // the kernel for batches of up to small_batch playouts
   int res_warps = 16;        // warps per CTA of the resident kernel (CAAA_WARPS)
-  int* d_abort = nullptr;    // watchdog flag of the resident kernel
   long long small_batch = 32768;  // batches up to this size go to the lockstep kernel (no pool hops: lower latency);
                                   // CAAA_ROLLOUT_KERNEL=stream sets it to 0
   int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
   int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
   int group_size = 16;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
-  void* d_pool = nullptr;    // game pools + group state of the phase-regrouped kernel
-  size_t pool_cap = 0;
-  GroupState* d_groups_last = nullptr;  // group state of the most recent launch (watchdog flag)
-  int n_groups_last = 0;
+  LaunchSlot slots[N_LAUNCH_SLOTS];  // per-launch scratch: launches on different streams may be in flight together
+  int next_slot = 0;
+  std::atomic_flag busy = ATOMIC_FLAG_INIT;  // the context is single-caller: concurrent entry is refused (CAAA_E_BUSY)
 };
 static Context g_ctx;
 static std::string g_err;
@@ -415,6 +474,16 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
   }
   return code;
 }
+// The context serves one caller at a time (like the reference API, whose engine lives in file-scope globals).
+// A second thread entering while a call is in progress is refused instead of corrupting the shared scratch.
+struct EntryGuard {
+  bool ok;
+  EntryGuard();
+  ~EntryGuard();
+};
+#define CAAA_ENTER()   \
+  EntryGuard entry_;   \
+  if (!entry_.ok) return CAAA_E_BUSY  /* caaa_gpu_last_error() keeps the message of the call in progress */
 #define CUDA_TRY(expr)                                             \
   do {                                                             \
     cudaError_t e_ = (expr);                                       \
@@ -430,6 +499,21 @@ static int grow(void** p, size_t* cap, size_t need) {
   *cap = need;
   return CAAA_OK;
 }
+EntryGuard::EntryGuard() : ok(!g_ctx.busy.test_and_set(std::memory_order_acquire)) {}
+EntryGuard::~EntryGuard() {
+  if (ok) g_ctx.busy.clear(std::memory_order_release);
+}
+
+// Every launch slot whose work has completed: did a kernel's watchdog give up?  (Call after a synchronisation.)
+static int check_watchdogs() {
+  for (LaunchSlot& l : g_ctx.slots) {
+    if (!l.used) continue;
+    int aborted = 0;
+    CUDA_TRY(cudaMemcpy(&aborted, l.d_abort, sizeof(int), cudaMemcpyDeviceToHost));
+    if (aborted) return fail(CAAA_E_CUDA, "rollout kernel stopped by its watchdog: no claimable game although the batch was unfinished");
+  }
+  return CAAA_OK;
+}
 static int small_smem() { return TABLE_BYTES + SMALL_THREADS * (int)sizeof(Game); }
 static int rollout_smem() { return TABLE_BYTES + ROLLOUT_THREADS * (int)sizeof(Game); }
 
@@ -437,22 +521,33 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
                           unsigned long long first_game_id, double* d_results, CaaaRolloutStats* d_stats,
                           CaaaBatchSummary* d_summary, cudaStream_t stream) {
   Context& c = g_ctx;
+  LaunchSlot& L = c.slots[c.next_slot];
+  c.next_slot = (c.next_slot + 1) % N_LAUNCH_SLOTS;
   const unsigned long long n_games = (unsigned long long)n_states * rollouts_per_state;
-  const size_t tmpl_bytes = (size_t)n_states * sizeof(Game);
-  int rc = grow(&c.d_templates, &c.templates_cap, tmpl_bytes + (size_t)n_states * sizeof(double));
-  if (rc != CAAA_OK) return rc;
-  uint32_t* d_tmpl = (uint32_t*)c.d_templates;
-  double* d_scores0 = (double*)((uint8_t*)c.d_templates + (tmpl_bytes + 7) / 8 * 8);
-  if ((tmpl_bytes + 7) / 8 * 8 + (size_t)n_states * sizeof(double) > c.templates_cap) {
-    rc = grow(&c.d_templates, &c.templates_cap, (tmpl_bytes + 7) / 8 * 8 + (size_t)n_states * sizeof(double));
-    if (rc != CAAA_OK) return rc;
-    d_tmpl = (uint32_t*)c.d_templates;
-    d_scores0 = (double*)((uint8_t*)c.d_templates + (tmpl_bytes + 7) / 8 * 8);
+  const size_t tmpl_bytes = ((size_t)n_states * sizeof(Game) + 7) / 8 * 8;
+  const size_t tmpl_need = tmpl_bytes + (size_t)n_states * sizeof(double);
+  const size_t pool_need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game) + 16 +
+                           (size_t)((c.sm_count + c.group_size - 1) / c.group_size) * sizeof(GroupState) + sizeof(StreamDbg) + sizeof(ResDbg);
+  if (L.used) {
+    if (tmpl_need > L.templates_cap || pool_need > L.pool_cap) CUDA_TRY(cudaEventSynchronize(L.done));  // buffers are about to be replaced
+    else CUDA_TRY(cudaStreamWaitEvent(stream, L.done, 0));  // the previous launch that used this slot must have drained (device-side wait)
   }
+  int rc = grow(&L.d_templates, &L.templates_cap, tmpl_need);
+  if (rc != CAAA_OK) return rc;
+  if ((rc = grow(&L.d_pool, &L.pool_cap, pool_need)) != CAAA_OK) return rc;
+  uint32_t* d_tmpl = (uint32_t*)L.d_templates;
+  double* d_scores0 = (double*)((uint8_t*)L.d_templates + tmpl_bytes);
+  L.used = true;
+  struct RecordDone {  // whatever path returns, the slot's event marks the end of this launch's work on `stream`
+    LaunchSlot& l;
+    cudaStream_t st;
+    ~RecordDone() { cudaEventRecord(l.done, st); }
+  } record_done{L, stream};
   prepare_kernel<<<(n_states + SMALL_THREADS - 1) / SMALL_THREADS, SMALL_THREADS, small_smem(), stream>>>(
       c.d_tables, (const uint8_t*)d_states, n_states, d_tmpl, d_scores0);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemsetAsync(c.d_ticket, 0, sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(L.d_ticket, 0, sizeof(unsigned long long), stream));
+  CUDA_TRY(cudaMemsetAsync(L.d_abort, 0, sizeof(int), stream));
   RolloutArgs a;
   a.tables = c.d_tables;
   a.templates = d_tmpl;
@@ -464,7 +559,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.results = d_results;
   a.stats = d_stats;
   a.summary = d_summary;
-  a.ticket = c.d_ticket;
+  a.ticket = L.d_ticket;
   {
     const char* sb = std::getenv("CAAA_SWITCH_BELOW");
     a.switch_below = sb ? std::atoi(sb) : 8;
@@ -485,7 +580,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.min_batch = env_int("CAAA_MIN_BATCH", 1);
   a.min_batch_polls = env_int("CAAA_MIN_BATCH_POLLS", 8);
   a.idle_ns = (unsigned)env_int("CAAA_IDLE_NS", 100);
-  a.abort_flag = c.d_abort;
+  a.abort_flag = L.d_abort;
   {  // which kernel: CAAA_ROLLOUT_KERNEL = resident | stream | lockstep forces one; default = by batch size
     const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
     const long long small = env_int("CAAA_SMALL_BATCH", (int)c.small_batch);
@@ -497,19 +592,17 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   if (c.kernel == 0) {
     // SM-resident kernel: spread small batches over all SMs (latency), fill every slot for large ones (regrouping)
     const unsigned long long want32 = (n_games + 31) / 32;
-    const int grid_r = (int)(want32 < (unsigned long long)c.sm_count ? want32 : (unsigned long long)c.sm_count);
+    const unsigned long long sms_r = (unsigned long long)(c.rollout_sms > 0 && c.rollout_sms < c.sm_count ? c.rollout_sms : c.sm_count);
+    const int grid_r = (int)(want32 < sms_r ? want32 : sms_r);
     const unsigned long long per_cta = (n_games + grid_r - 1) / grid_r;
     int n_slots = (int)((per_cta + 31) / 32 * 32);
     if (n_slots > RES_SLOTS) n_slots = RES_SLOTS;
     if (n_slots < 32) n_slots = 32;
     ResDbg* d_dbg = nullptr;
     if (std::getenv("CAAA_DEBUG") != nullptr) {
-      int rc2 = grow(&c.d_pool, &c.pool_cap, sizeof(ResDbg));
-      if (rc2 != CAAA_OK) return rc2;
-      d_dbg = (ResDbg*)c.d_pool;
+      d_dbg = (ResDbg*)L.d_pool;
       CUDA_TRY(cudaMemsetAsync(d_dbg, 0, sizeof(ResDbg), stream));
     }
-    CUDA_TRY(cudaMemsetAsync(c.d_abort, 0, sizeof(int), stream));
     int res_warps = env_int("CAAA_WARPS", c.res_warps);
     if (res_warps < 1) res_warps = 1;
     if (res_warps > 32) res_warps = 32;
@@ -545,32 +638,29 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     return CAAA_OK;
   }
   const unsigned long long want = (n_games + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;
-  const int grid = (int)(want < (unsigned long long)c.sm_count ? want : (unsigned long long)c.sm_count);
+  const unsigned long long sms = (unsigned long long)(c.rollout_sms > 0 && c.rollout_sms < c.sm_count ? c.rollout_sms : c.sm_count);
+  const int grid = (int)(want < sms ? want : sms);
   if (c.kernel == 1) {
     const size_t need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game);
     const int n_groups = (grid + c.group_size - 1) / c.group_size;
     const size_t need16 = (need + 15) / 16 * 16;
-    int rc2 = grow(&c.d_pool, &c.pool_cap, need16 + (size_t)n_groups * sizeof(GroupState) + sizeof(StreamDbg));
-    if (rc2 != CAAA_OK) return rc2;
-    GroupState* d_groups = (GroupState*)((uint8_t*)c.d_pool + need16);
+    GroupState* d_groups = (GroupState*)((uint8_t*)L.d_pool + need16);
     group_init_kernel<<<n_groups, 256, 0, stream>>>(d_groups, n_groups, STREAM_SLOTS * c.pool_mult, c.group_size, grid);
     StreamDbg* d_dbg = nullptr;
     if (std::getenv("CAAA_DEBUG") != nullptr) {
       d_dbg = (StreamDbg*)((uint8_t*)d_groups + (size_t)n_groups * sizeof(GroupState));
       CUDA_TRY(cudaMemsetAsync(d_dbg, 0, sizeof(StreamDbg), stream));
     }
-#define CAAA_LAUNCH_STREAM(L)                                                                                                        \
+#define CAAA_LAUNCH_STREAM(NL)                                                                                                       \
   do {                                                                                                                              \
     if (d_stats)                                                                                                                    \
-      rollout_kernel_stream<true, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg);  \
+      rollout_kernel_stream<true, NL><<<grid, STREAM_SLOTS / NL * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg);  \
     else                                                                                                                            \
-      rollout_kernel_stream<false, L><<<grid, STREAM_SLOTS / L * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)c.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
+      rollout_kernel_stream<false, NL><<<grid, STREAM_SLOTS / NL * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
   } while (0)
     if (c.lanes == 32) CAAA_LAUNCH_STREAM(32);
     else if (c.lanes == 8) CAAA_LAUNCH_STREAM(8);
     else CAAA_LAUNCH_STREAM(16);
-    c.d_groups_last = d_groups;
-    c.n_groups_last = n_groups;
     if (d_dbg != nullptr) {
       StreamDbg h;
       cudaStreamSynchronize(stream);
@@ -622,10 +712,13 @@ int caaa_gpu_init(int device) {
   build_dev_tables(&c.host_tables);
   CUDA_TRY(cudaMalloc(&c.d_tables, sizeof(DevTables)));
   CUDA_TRY(cudaMemcpy(c.d_tables, &c.host_tables, sizeof(DevTables), cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&c.d_ticket, sizeof(unsigned long long)));
+  for (LaunchSlot& l : c.slots) {
+    CUDA_TRY(cudaMalloc(&l.d_ticket, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&l.d_abort, sizeof(int)));
+    CUDA_TRY(cudaMemset(l.d_abort, 0, sizeof(int)));
+    CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaMalloc(&c.d_summary, sizeof(CaaaBatchSummary)));
-  CUDA_TRY(cudaMalloc(&c.d_abort, sizeof(int)));
-  CUDA_TRY(cudaMemset(c.d_abort, 0, sizeof(int)));
   CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&c.ev0));
   CUDA_TRY(cudaEventCreate(&c.ev1));
@@ -666,7 +759,7 @@ int caaa_gpu_init(int device) {
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   CUDA_TRY(cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
-  CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
+  CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BATTLE_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(actions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
@@ -679,19 +772,59 @@ int caaa_gpu_shutdown(void) {
   if (!c.ready) return CAAA_OK;
   cudaStreamSynchronize(c.stream);
   cudaFree(c.d_tables);
-  cudaFree(c.d_ticket);
+  for (LaunchSlot& l : c.slots) {
+    if (l.used) cudaEventSynchronize(l.done);
+    cudaFree(l.d_ticket);
+    cudaFree(l.d_abort);
+    if (l.d_templates) cudaFree(l.d_templates);
+    if (l.d_pool) cudaFree(l.d_pool);
+    cudaEventDestroy(l.done);
+  }
   cudaFree(c.d_summary);
-  cudaFree(c.d_abort);
+  for (LeafBatch& b : c.leaf) {
+    if (!b.ready) continue;
+    cudaStreamSynchronize(b.stream);
+    if (b.h_in) cudaFreeHost(b.h_in);
+    if (b.h_out) cudaFreeHost(b.h_out);
+    if (b.d_in) cudaFree(b.d_in);
+    if (b.d_out) cudaFree(b.d_out);
+    if (b.d_targets) cudaFree(b.d_targets);
+    if (b.d_results) cudaFree(b.d_results);
+    cudaFree(b.d_summary);
+    cudaEventDestroy(b.done);
+    cudaStreamDestroy(b.stream);
+    b = LeafBatch();
+  }
+  if (c.battle.ready)
+    for (int b = 0; b < BattlePipe::NBUF; b++) {
+      cudaFreeHost(c.battle.h_in[b]);
+      cudaFreeHost(c.battle.h_out[b]);
+      cudaFreeHost(c.battle.h_draws[b]);
+      cudaFree(c.battle.d_in[b]);
+      cudaFree(c.battle.d_out[b]);
+      cudaFree(c.battle.d_draws[b]);
+      cudaStreamDestroy(c.battle.stream[b]);
+      cudaEventDestroy(c.battle.k0[b]);
+      cudaEventDestroy(c.battle.k1[b]);
+      cudaEventDestroy(c.battle.done[b]);
+    }
   if (c.d_in) cudaFree(c.d_in);
   if (c.d_out) cudaFree(c.d_out);
   if (c.d_aux) cudaFree(c.d_aux);
   if (c.d_aux2) cudaFree(c.d_aux2);
-  if (c.d_templates) cudaFree(c.d_templates);
-  if (c.d_pool) cudaFree(c.d_pool);
   cudaEventDestroy(c.ev0);
   cudaEventDestroy(c.ev1);
   cudaStreamDestroy(c.stream);
-  c = Context();
+  c.ready = false;
+  c.battle = BattlePipe();
+  for (LaunchSlot& l : c.slots) l = LaunchSlot();
+  c.next_slot = 0;
+  c.d_tables = nullptr;
+  c.d_summary = nullptr;
+  c.d_in = c.d_out = c.d_aux = c.d_aux2 = nullptr;
+  c.in_cap = c.out_cap = c.aux_cap = c.aux2_cap = 0;
+  c.stream = nullptr;
+  c.ev0 = c.ev1 = nullptr;
   return CAAA_OK;
 }
 
@@ -717,6 +850,7 @@ int caaa_gpu_device_info(int* sm_count, int* max_smem_per_block, char* name64) {
 int caaa_gpu_rollout_batch_device(const void* d_states, int n_states, int rollouts_per_state, uint64_t seed,
                                   uint64_t first_game_id, double* d_results, CaaaRolloutStats* d_stats,
                                   CaaaBatchSummary* d_summary, void* cuda_stream) {
+  CAAA_ENTER();
   if (!g_ctx.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!d_states || !d_results || n_states <= 0 || rollouts_per_state <= 0) return fail(CAAA_E_ARG, "bad rollout batch arguments");
   return launch_rollout(d_states, n_states, (unsigned)rollouts_per_state, seed, first_game_id, d_results, d_stats, d_summary,
@@ -725,6 +859,7 @@ int caaa_gpu_rollout_batch_device(const void* d_states, int n_states, int rollou
 
 int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollouts_per_state, uint64_t seed,
                            uint64_t first_game_id, double* results, CaaaRolloutStats* stats, CaaaBatchSummary* summary) {
+  CAAA_ENTER();
   Context& c = g_ctx;
   if (!c.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!states || !results || n_states <= 0 || rollouts_per_state <= 0) return fail(CAAA_E_ARG, "bad rollout batch arguments");
@@ -746,15 +881,9 @@ int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollou
   CaaaBatchSummary s;
   CUDA_TRY(cudaMemcpyAsync(&s, c.d_summary, sizeof(s), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
-  if (c.kernel == 0) {
-    int aborted = 0;
-    CUDA_TRY(cudaMemcpy(&aborted, c.d_abort, sizeof(int), cudaMemcpyDeviceToHost));
-    if (aborted) return fail(CAAA_E_CUDA, "rollout kernel stopped by its watchdog: no claimable game although the batch was unfinished");
-  }
-  for (int gidx = 0; c.kernel == 1 && gidx < c.n_groups_last; gidx++) {  // watchdog of the phase-regrouped kernel
-    int aborted = 0;
-    CUDA_TRY(cudaMemcpy(&aborted, &c.d_groups_last[gidx].aborted, sizeof(int), cudaMemcpyDeviceToHost));
-    if (aborted) return fail(CAAA_E_CUDA, "rollout kernel stopped by its watchdog: no claimable game although the batch was unfinished");
+  {
+    const int rc_w = check_watchdogs();
+    if (rc_w != CAAA_OK) return rc_w;
   }
   if (s.playouts != (unsigned long long)n_games) return fail(CAAA_E_CUDA, "rollout kernel finished fewer playouts than requested");
   if (summary) {
@@ -764,6 +893,14 @@ int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollou
     *summary = s;
   }
   return CAAA_OK;
+}
+
+int caaa_gpu_synchronize(void) {
+  CAAA_ENTER();
+  if (!g_ctx.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
+  for (LaunchSlot& l : g_ctx.slots)
+    if (l.used) CUDA_TRY(cudaEventSynchronize(l.done));
+  return check_watchdogs();
 }
 
 int caaa_gpu_set_stream(uint64_t seed, uint64_t next_game_id) {
@@ -781,6 +918,7 @@ double caaa_gpu_random_play_until_terminal(const CaaaGameState* state) {
 
 int caaa_gpu_advance(const CaaaGameState* states, int n, uint64_t seed, uint64_t first_game_id, int n_turns,
                      CaaaGameState* out_states, CaaaCacheDump* out_caches, int32_t* out_draws) {
+  CAAA_ENTER();
   Context& c = g_ctx;
   if (!c.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!states || n <= 0 || n_turns < 0) return fail(CAAA_E_ARG, "bad advance arguments");
@@ -802,33 +940,135 @@ int caaa_gpu_advance(const CaaaGameState* states, int n, uint64_t seed, uint64_t
   return CAAA_OK;
 }
 
+static void launch_battles(const void* d_states, int n, uint64_t seed, uint64_t first_game_id, void* d_out, int32_t* d_draws,
+                           CaaaBatchSummary* d_summary, cudaStream_t stream) {
+  Context& c = g_ctx;
+  const int tiles = (n + TILE_STATES - 1) / TILE_STATES;
+  int grid = (tiles + BATTLE_WARPS - 1) / BATTLE_WARPS;
+  if (grid > c.sm_count * 8) grid = c.sm_count * 8;  // warps loop over tiles; a multiple of the SM count
+  battle_kernel<<<grid, BATTLE_WARPS * 32, BATTLE_SMEM, stream>>>(c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id,
+                                                                  (uint8_t*)d_out, d_draws, d_summary);
+}
+
+int caaa_gpu_resolve_battles_device(const void* d_states, int n, uint64_t seed, uint64_t first_game_id, void* d_out_states,
+                                    int32_t* d_out_draws, CaaaBatchSummary* d_summary, void* cuda_stream) {
+  CAAA_ENTER();
+  if (!g_ctx.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
+  if (!d_states || n <= 0) return fail(CAAA_E_ARG, "bad battle arguments");
+  launch_battles(d_states, n, seed, first_game_id, d_out_states, d_out_draws, d_summary, (cudaStream_t)cuda_stream);
+  CUDA_TRY(cudaGetLastError());
+  return CAAA_OK;
+}
+
+// Host-buffer form: chunks of BATTLE_CHUNK states flow through three pinned staging buffers and three streams, so the
+// host->pinned copy of chunk c+1, the H2D / kernel / D2H of chunk c and the pinned->host copy of chunk c-1 overlap
+// (pageable user buffers cannot be copied asynchronously themselves).
 int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, uint64_t first_game_id,
                              CaaaGameState* out_states, int32_t* out_draws, CaaaBatchSummary* summary) {
+  CAAA_ENTER();
   Context& c = g_ctx;
   if (!c.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!states || n <= 0) return fail(CAAA_E_ARG, "bad battle arguments");
-  const size_t bytes = (size_t)n * CAAA_STATE_BYTES;
-  int rc;
-  if ((rc = grow(&c.d_in, &c.in_cap, bytes)) != CAAA_OK) return rc;
-  if ((rc = grow(&c.d_out, &c.out_cap, bytes)) != CAAA_OK) return rc;
-  if ((rc = grow(&c.d_aux2, &c.aux2_cap, (size_t)n * sizeof(int32_t))) != CAAA_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(c.d_in, states, bytes, cudaMemcpyHostToDevice, c.stream));
+  BattlePipe& bp = c.battle;
+  const size_t chunk = BATTLE_CHUNK;
+  if (!bp.ready) {
+    for (int b = 0; b < BattlePipe::NBUF; b++) {
+      CUDA_TRY(cudaHostAlloc(&bp.h_in[b], chunk * CAAA_STATE_BYTES, cudaHostAllocDefault));
+      CUDA_TRY(cudaHostAlloc(&bp.h_out[b], chunk * CAAA_STATE_BYTES, cudaHostAllocDefault));
+      CUDA_TRY(cudaHostAlloc((void**)&bp.h_draws[b], chunk * sizeof(int32_t), cudaHostAllocDefault));
+      CUDA_TRY(cudaMalloc(&bp.d_in[b], chunk * CAAA_STATE_BYTES));
+      CUDA_TRY(cudaMalloc(&bp.d_out[b], chunk * CAAA_STATE_BYTES));
+      CUDA_TRY(cudaMalloc((void**)&bp.d_draws[b], chunk * sizeof(int32_t)));
+      CUDA_TRY(cudaStreamCreateWithFlags(&bp.stream[b], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreate(&bp.k0[b]));
+      CUDA_TRY(cudaEventCreate(&bp.k1[b]));
+      CUDA_TRY(cudaEventCreateWithFlags(&bp.done[b], cudaEventDisableTiming));
+    }
+    bp.ready = true;
+  }
   CUDA_TRY(cudaMemsetAsync(c.d_summary, 0, sizeof(CaaaBatchSummary), c.stream));
-  CUDA_TRY(cudaEventRecord(c.ev0, c.stream));
-  const int grid = (n + ROLLOUT_THREADS - 1) / ROLLOUT_THREADS;  // 7 warps per SM: the sweep is bound by per-warp latency
-  battle_kernel<<<grid, ROLLOUT_THREADS, rollout_smem(), c.stream>>>(c.d_tables, (const uint8_t*)c.d_in, n, seed, first_game_id,
-                                                                 (uint8_t*)c.d_out, (int32_t*)c.d_aux2, c.d_summary);
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(c.ev1, c.stream));
-  if (out_states) CUDA_TRY(cudaMemcpyAsync(out_states, c.d_out, bytes, cudaMemcpyDeviceToHost, c.stream));
-  if (out_draws) CUDA_TRY(cudaMemcpyAsync(out_draws, c.d_aux2, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
-  CaaaBatchSummary s;
-  CUDA_TRY(cudaMemcpyAsync(&s, c.d_summary, sizeof(s), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
-  if (summary) {
+  const int n_chunks = (int)(((size_t)n + chunk - 1) / chunk);
+  std::mutex mu;
+  std::condition_variable cv;
+  int issued = 0, drained = 0;
+  bool failed = false;
+  double kernel_ms = 0.0;
+  // drains chunk k: waits for its D2H, copies the pinned results to the caller's buffers
+  auto drain = [&](int k) -> bool {
+    const int b = k % BattlePipe::NBUF;
+    const size_t lo = (size_t)k * chunk, cnt = std::min(chunk, (size_t)n - lo);
+    if (cudaEventSynchronize(bp.done[b]) != cudaSuccess) return false;
+    if (out_states) std::memcpy((uint8_t*)out_states + lo * CAAA_STATE_BYTES, bp.h_out[b], cnt * CAAA_STATE_BYTES);
+    if (out_draws) std::memcpy(out_draws + lo, bp.h_draws[b], cnt * sizeof(int32_t));
     float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
-    s.kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, bp.k0[b], bp.k1[b]) == cudaSuccess) kernel_ms += ms;
+    return true;
+  };
+  std::thread drainer;
+  const bool threaded = n_chunks > 1;
+  if (threaded)
+    drainer = std::thread([&] {
+      for (int k = 0; k < n_chunks; k++) {
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return issued > k || failed; });
+          if (failed) return;
+        }
+        const bool ok = drain(k);
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ok) failed = true;
+        drained = k + 1;
+        cv.notify_all();
+        if (!ok) return;
+      }
+    });
+  int rc = CAAA_OK;
+  for (int k = 0; k < n_chunks && rc == CAAA_OK; k++) {
+    const int b = k % BattlePipe::NBUF;
+    const size_t lo = (size_t)k * chunk, cnt = std::min(chunk, (size_t)n - lo);
+    if (threaded && k >= BattlePipe::NBUF) {  // buffer b is free once chunk k - NBUF has been drained
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return drained > k - BattlePipe::NBUF || failed; });
+      if (failed) break;
+    }
+    std::memcpy(bp.h_in[b], (const uint8_t*)states + lo * CAAA_STATE_BYTES, cnt * CAAA_STATE_BYTES);
+    cudaStream_t st = bp.stream[b];
+    cudaError_t e = cudaMemcpyAsync(bp.d_in[b], bp.h_in[b], cnt * CAAA_STATE_BYTES, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaEventRecord(bp.k0[b], st);
+    if (e == cudaSuccess) {
+      launch_battles(bp.d_in[b], (int)cnt, seed, first_game_id + lo, out_states ? bp.d_out[b] : nullptr, bp.d_draws[b], c.d_summary, st);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(bp.k1[b], st);
+    if (e == cudaSuccess && out_states) e = cudaMemcpyAsync(bp.h_out[b], bp.d_out[b], cnt * CAAA_STATE_BYTES, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_draws) e = cudaMemcpyAsync(bp.h_draws[b], bp.d_draws[b], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(bp.done[b], st);
+    if (e != cudaSuccess) rc = fail(CAAA_E_CUDA, "battle pipeline", e);
+    if (threaded) {
+      std::lock_guard<std::mutex> lk(mu);
+      if (rc != CAAA_OK) failed = true;
+      else issued = k + 1;
+      cv.notify_all();
+    } else if (rc == CAAA_OK && !drain(k)) {
+      rc = fail(CAAA_E_CUDA, "battle pipeline: device error", cudaGetLastError());
+    }
+  }
+  if (threaded) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (rc != CAAA_OK) failed = true;
+      cv.notify_all();
+    }
+    drainer.join();
+    if (failed && rc == CAAA_OK) rc = fail(CAAA_E_CUDA, "battle pipeline: device error", cudaGetLastError());
+  }
+  if (rc != CAAA_OK) return rc;
+  CaaaBatchSummary s;
+  CUDA_TRY(cudaMemcpy(&s, c.d_summary, sizeof(s), cudaMemcpyDeviceToHost));
+  if (s.playouts != (unsigned long long)n) return fail(CAAA_E_CUDA, "battle kernel resolved fewer states than requested");
+  if (summary) {
+    s.kernel_ms = kernel_ms;
     *summary = s;
   }
   return CAAA_OK;
@@ -836,6 +1076,7 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
 
 int caaa_gpu_expand(const CaaaGameState* leaves, int n, uint8_t* n_actions, uint8_t* actions, CaaaGameState* children,
                     uint32_t* status) {
+  CAAA_ENTER();
   Context& c = g_ctx;
   if (!c.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!leaves || !n_actions || !actions || n <= 0) return fail(CAAA_E_ARG, "bad expand arguments");
@@ -866,6 +1107,7 @@ int caaa_gpu_expand(const CaaaGameState* leaves, int n, uint8_t* n_actions, uint
 }
 
 int caaa_gpu_evaluate(const CaaaGameState* states, int n, double* scores) {
+  CAAA_ENTER();
   Context& c = g_ctx;
   if (!c.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!states || !scores || n <= 0) return fail(CAAA_E_ARG, "bad evaluate arguments");
@@ -879,6 +1121,142 @@ int caaa_gpu_evaluate(const CaaaGameState* states, int n, double* scores) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(scores, c.d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
+  return CAAA_OK;
+}
+
+// ---- asynchronous MCTS leaf batches ----
+// Layout of the pinned / device output block of a batch of n leaves.
+struct LeafOut {
+  size_t scores, sums, status, picked, n_actions, actions, children, total;
+  explicit LeafOut(size_t n) {
+    size_t o = 0;
+    scores = o; o += n * sizeof(double);
+    sums = o; o += n * sizeof(double);
+    status = o; o += n * sizeof(uint32_t);
+    picked = o; o += n * sizeof(int32_t);
+    n_actions = o; o += (n + 15) / 16 * 16;
+    actions = o; o += n * CAAA_ACTIONS;
+    o = (o + 15) / 16 * 16;
+    children = o; o += n * CAAA_ACTIONS * CAAA_STATE_BYTES;
+    total = o;
+  }
+};
+static size_t leaf_in_bytes(size_t n) { return (n * CAAA_STATE_BYTES + 15) / 16 * 16 + n * sizeof(uint64_t); }
+
+static int leaf_batch_reserve(LeafBatch& b, int n, size_t n_results) {
+  if (!b.ready) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+    CUDA_TRY(cudaMalloc(&b.d_summary, sizeof(CaaaBatchSummary)));
+    b.ready = true;
+  }
+  if (n > b.cap) {
+    int cap = b.cap ? b.cap : 64;
+    while (cap < n) cap *= 2;
+    if (b.h_in) cudaFreeHost(b.h_in);
+    if (b.h_out) cudaFreeHost(b.h_out);
+    if (b.d_in) cudaFree(b.d_in);
+    if (b.d_out) cudaFree(b.d_out);
+    if (b.d_targets) cudaFree(b.d_targets);
+    b.h_in = b.h_out = b.d_in = b.d_out = b.d_targets = nullptr;
+    b.cap = 0;
+    const LeafOut lo((size_t)cap);
+    CUDA_TRY(cudaHostAlloc((void**)&b.h_in, leaf_in_bytes((size_t)cap), cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc((void**)&b.h_out, lo.total, cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc((void**)&b.d_in, leaf_in_bytes((size_t)cap)));
+    CUDA_TRY(cudaMalloc((void**)&b.d_out, lo.total));
+    CUDA_TRY(cudaMalloc((void**)&b.d_targets, (size_t)cap * CAAA_STATE_BYTES));
+    b.cap = cap;
+  }
+  if (n_results > b.results_cap) {
+    if (b.d_results) cudaFree(b.d_results);
+    b.d_results = nullptr;
+    b.results_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&b.d_results, n_results * sizeof(double)));
+    b.results_cap = n_results;
+  }
+  return CAAA_OK;
+}
+
+int caaa_gpu_set_rollout_sms(int sms) {
+  CAAA_ENTER();
+  g_ctx.rollout_sms = sms < 0 ? 0 : sms;
+  return CAAA_OK;
+}
+
+int caaa_gpu_leaf_batch_submit(int handle, const CaaaGameState* leaves, int n, int rollouts_per_leaf, uint64_t seed,
+                               uint64_t first_game_id, const uint64_t* child_pick) {
+  CAAA_ENTER();
+  Context& c = g_ctx;
+  if (!c.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
+  if (handle < 0 || handle >= N_LEAF_BATCHES || !leaves || !child_pick || n <= 0 || rollouts_per_leaf <= 0)
+    return fail(CAAA_E_ARG, "bad leaf batch arguments");
+  LeafBatch& b = c.leaf[handle];
+  if (b.in_flight) return fail(CAAA_E_ARG, "leaf batch handle is still in flight: collect it first");
+  int rc = leaf_batch_reserve(b, n, (size_t)n * (size_t)rollouts_per_leaf);
+  if (rc != CAAA_OK) return rc;
+  const LeafOut lo((size_t)b.cap);
+  const size_t state_bytes = (size_t)n * CAAA_STATE_BYTES, pick_off = ((size_t)b.cap * CAAA_STATE_BYTES + 15) / 16 * 16;
+  std::memcpy(b.h_in, leaves, state_bytes);
+  std::memcpy(b.h_in + pick_off, child_pick, (size_t)n * sizeof(uint64_t));
+  cudaStream_t st = b.stream;
+  CUDA_TRY(cudaMemcpyAsync(b.d_in, b.h_in, state_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(b.d_in + pick_off, b.h_in + pick_off, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(b.d_summary, 0, sizeof(CaaaBatchSummary), st));
+  double* d_scores = (double*)(b.d_out + lo.scores);
+  double* d_sums = (double*)(b.d_out + lo.sums);
+  uint32_t* d_status = (uint32_t*)(b.d_out + lo.status);
+  int32_t* d_picked = (int32_t*)(b.d_out + lo.picked);
+  uint8_t* d_nact = b.d_out + lo.n_actions;
+  uint8_t* d_act = b.d_out + lo.actions;
+  uint8_t* d_children = b.d_out + lo.children;
+  const int blocks = (n + SMALL_THREADS - 1) / SMALL_THREADS;
+  evaluate_kernel<<<blocks, SMALL_THREADS, small_smem(), st>>>(c.d_tables, b.d_in, n, d_scores);
+  CUDA_TRY(cudaMemsetAsync(d_status, 0, (size_t)n * sizeof(uint32_t), st));
+  actions_kernel<<<blocks, SMALL_THREADS, small_smem(), st>>>(c.d_tables, b.d_in, n, d_nact, d_act, d_status);
+  const long long total = (long long)n * CAAA_ACTIONS;
+  apply_kernel<<<(int)((total + SMALL_THREADS - 1) / SMALL_THREADS), SMALL_THREADS, small_smem(), st>>>(c.d_tables, b.d_in, n, d_nact, d_act,
+                                                                                                     d_children, d_status);
+  pick_kernel<<<n, 128, 0, st>>>(b.d_in, n, d_scores, d_nact, d_status, (const uint64_t*)(b.d_in + pick_off), d_children, b.d_targets, d_picked);
+  CUDA_TRY(cudaGetLastError());
+  rc = launch_rollout(b.d_targets, n, (unsigned)rollouts_per_leaf, seed, first_game_id, b.d_results, nullptr, b.d_summary, st);
+  if (rc != CAAA_OK) return rc;
+  reduce_results_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(b.d_results, n, rollouts_per_leaf, d_sums);
+  CUDA_TRY(cudaGetLastError());
+  // one D2H for everything the host needs (children are only read up to n_actions per leaf, but arrive in one copy)
+  const LeafOut ln((size_t)b.cap);
+  CUDA_TRY(cudaMemcpyAsync(b.h_out, b.d_out, ln.children, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(b.h_out + ln.children, b.d_out + ln.children, (size_t)n * CAAA_ACTIONS * CAAA_STATE_BYTES, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(b.done, st));
+  b.n = n;
+  b.in_flight = true;
+  return CAAA_OK;
+}
+
+int caaa_gpu_leaf_batch_collect(int handle, double* scores, uint8_t* n_actions, uint8_t* actions, CaaaGameState* children,
+                                uint32_t* status, int32_t* picked, double* sum_results, CaaaBatchSummary* summary) {
+  CAAA_ENTER();
+  Context& c = g_ctx;
+  if (!c.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
+  if (handle < 0 || handle >= N_LEAF_BATCHES) return fail(CAAA_E_ARG, "bad leaf batch handle");
+  LeafBatch& b = c.leaf[handle];
+  if (!b.in_flight) return fail(CAAA_E_ARG, "leaf batch handle has nothing in flight");
+  CUDA_TRY(cudaEventSynchronize(b.done));
+  b.in_flight = false;
+  const size_t n = (size_t)b.n;
+  const LeafOut lo((size_t)b.cap);
+  if (scores) std::memcpy(scores, b.h_out + lo.scores, n * sizeof(double));
+  if (sum_results) std::memcpy(sum_results, b.h_out + lo.sums, n * sizeof(double));
+  if (status) std::memcpy(status, b.h_out + lo.status, n * sizeof(uint32_t));
+  if (picked) std::memcpy(picked, b.h_out + lo.picked, n * sizeof(int32_t));
+  if (n_actions) std::memcpy(n_actions, b.h_out + lo.n_actions, n);
+  if (actions) std::memcpy(actions, b.h_out + lo.actions, n * CAAA_ACTIONS);
+  if (children) std::memcpy(children, b.h_out + lo.children, n * CAAA_ACTIONS * CAAA_STATE_BYTES);
+  CaaaBatchSummary s;
+  CUDA_TRY(cudaMemcpy(&s, b.d_summary, sizeof(s), cudaMemcpyDeviceToHost));
+  const int rc_w = check_watchdogs();
+  if (rc_w != CAAA_OK) return rc_w;
+  if (summary) *summary = s;
   return CAAA_OK;
 }
 

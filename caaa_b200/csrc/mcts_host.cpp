@@ -6,8 +6,8 @@
 // node accumulates `result` when its parent's player_index is even and `1 - result` otherwise
 // (mcts.cpp:96-105).  What changes is where the work runs: expansion (get_possible_actions +
 // apply_action per action) and rollouts are batched device calls, `rollouts_per_leaf` playouts are
-// played per visited leaf (BASELINE config 4: 4096) and `leaves_per_batch` leaves are selected per
-// launch with virtual visits so one host thread keeps the GPU busy.  With both set to 1 the loop is
+// played per visited leaf (BASELINE config 4: 4096), `leaves_per_batch` leaves are selected per launch with
+// virtual visits, and two such batches are kept in flight so one host thread keeps the GPU busy.  With both set to 1 the loop is
 // the reference's, except that is_terminal_state is evaluated on the node's own unit totals (the
 // reference reads stale globals there) and the random stream is Philox.
 #include <cmath>
@@ -76,71 +76,101 @@ void backpropagate(Node* node, double sum_result, int64_t n) {  // reference src
 
 }  // namespace
 
-extern "C" int caaa_mcts_search(const CaaaGameState* root_state, int64_t iterations, int rollouts_per_leaf,
-                                int leaves_per_batch, uint64_t seed, CaaaRootStats* out, uint8_t* best_action) {
-  if (!root_state || !out || iterations < 0 || rollouts_per_leaf <= 0 || leaves_per_batch <= 0) return CAAA_E_ARG;
+// Pipelined driver: up to `depth` leaf batches are in flight (caaa_gpu_leaf_batch_submit / _collect).  While batch k rolls
+// out on the device, the host back-propagates batch k-1 and selects batch k+1 with virtual visits standing in for the
+// results that are still outstanding; expansion, the random child and the per-leaf sums all stay on the device.
+extern "C" int caaa_mcts_search_pipelined(const CaaaGameState* root_state, int64_t iterations, int rollouts_per_leaf,
+                                          int leaves_per_batch, int depth, uint64_t seed, CaaaRootStats* out, uint8_t* best_action) {
+  if (!root_state || !out || iterations < 0 || rollouts_per_leaf <= 0 || leaves_per_batch <= 0 || depth < 1 || depth > 3) return CAAA_E_ARG;
   Tree tree;
   Node* root = tree.make(*root_state, 0, nullptr);
   std::mt19937_64 rng(seed ^ 0x9E3779B97F4A7C15ull);
   uint64_t next_game_id = 0;
-  int64_t done = 0, playouts = 0;
-  std::vector<Node*> leaves, targets;
+  int64_t done = 0, selected = 0, playouts = 0;
+  struct Flight {
+    int handle;
+    std::vector<Node*> leaves;
+  };
+  std::deque<Flight> flights;
+  std::vector<int> free_handles;
+  for (int h = depth - 1; h >= 0; h--) free_handles.push_back(h);
   std::vector<CaaaGameState> states, children;
-  std::vector<double> scores, results;
+  std::vector<double> scores, sums;
   std::vector<uint8_t> n_actions, actions;
   std::vector<uint32_t> status;
-  while (done < iterations) {
-    // 1. select up to leaves_per_batch distinct leaves, marking virtual visits along their paths
-    leaves.clear();
-    const int64_t want = std::min<int64_t>(leaves_per_batch, iterations - done);
-    for (int64_t b = 0; b < want; b++) {
-      Node* leaf = select_best_leaf(root);
-      if (leaf->in_batch) break;  // the tree offers no further distinct leaf right now
-      leaf->in_batch = true;
-      for (Node* n = leaf; n != nullptr; n = n->parent) n->pending += rollouts_per_leaf;  // one visit = rollouts_per_leaf playouts
-      leaves.push_back(leaf);
+  std::vector<int32_t> picked;
+  std::vector<uint64_t> picks;
+  int sm_count = 0;
+  if (depth > 1 && caaa_gpu_device_info(&sm_count, nullptr, nullptr) == CAAA_OK && sm_count > 32)
+    caaa_gpu_set_rollout_sms((sm_count - 4) / 16 * 16);  // a few SMs stay free for the other batch's expansion kernels
+  int rc = CAAA_OK;
+  while (rc == CAAA_OK && (selected < iterations || !flights.empty())) {
+    // 1. keep `depth` batches in flight: select distinct leaves, marking virtual visits along their paths
+    while (!free_handles.empty() && selected < iterations) {
+      Flight f;
+      const int64_t want = std::min<int64_t>(leaves_per_batch, iterations - selected);
+      for (int64_t b = 0; b < want; b++) {
+        Node* leaf = select_best_leaf(root);
+        if (leaf->in_batch) break;  // the tree offers no further distinct leaf until a batch in flight has been collected
+        leaf->in_batch = true;
+        for (Node* n = leaf; n != nullptr; n = n->parent) n->pending += rollouts_per_leaf;  // one visit = rollouts_per_leaf playouts
+        f.leaves.push_back(leaf);
+      }
+      const int nl = (int)f.leaves.size();
+      if (nl == 0) break;
+      states.resize(nl);
+      picks.resize(nl);
+      for (int i = 0; i < nl; i++) {
+        states[i] = f.leaves[i]->state;
+        picks[i] = rng();  // `rand() % num_children`, reference src/mcts.cpp:86 (the modulo is taken on the device)
+      }
+      f.handle = free_handles.back();
+      rc = caaa_gpu_leaf_batch_submit(f.handle, states.data(), nl, rollouts_per_leaf, seed, next_game_id, picks.data());
+      if (rc != CAAA_OK) break;
+      free_handles.pop_back();
+      next_game_id += (uint64_t)nl * (uint64_t)rollouts_per_leaf;
+      selected += nl;
+      flights.push_back(std::move(f));
     }
-    const int nl = (int)leaves.size();
-    // 2. terminal test and expansion of all selected leaves in one device call each
-    states.resize(nl);
-    for (int i = 0; i < nl; i++) states[i] = leaves[i]->state;
+    if (rc != CAAA_OK || flights.empty()) break;
+    // 2. collect the oldest batch: grow the tree, clear its virtual visits, back-propagate the per-leaf sums
+    Flight f = std::move(flights.front());
+    flights.pop_front();
+    const int nl = (int)f.leaves.size();
     scores.resize(nl);
-    int rc = caaa_gpu_evaluate(states.data(), nl, scores.data());
-    if (rc != CAAA_OK) return rc;
-    n_actions.assign(nl, 0);
-    actions.assign((size_t)nl * CAAA_ACTIONS, 0);
+    sums.resize(nl);
+    n_actions.resize(nl);
+    actions.resize((size_t)nl * CAAA_ACTIONS);
     children.resize((size_t)nl * CAAA_ACTIONS);
-    status.assign(nl, 0);
-    rc = caaa_gpu_expand(states.data(), nl, n_actions.data(), actions.data(), children.data(), status.data());
-    if (rc != CAAA_OK) return rc;
-    targets.assign(nl, nullptr);
+    status.resize(nl);
+    picked.resize(nl);
+    rc = caaa_gpu_leaf_batch_collect(f.handle, scores.data(), n_actions.data(), actions.data(), children.data(), status.data(),
+                                     picked.data(), sums.data(), nullptr);
+    free_handles.push_back(f.handle);
+    if (rc != CAAA_OK) break;
     for (int i = 0; i < nl; i++) {
-      Node* leaf = leaves[i];
+      Node* leaf = f.leaves[i];
+      Node* target = leaf;
       const bool terminal = scores[i] > 0.99 || scores[i] < 0.01;  // reference src/engine.cpp:4244-4248
       if (!terminal && !(status[i] & 0x80000000u)) {
         for (int k = 0; k < n_actions[i]; k++) {
           if (status[i] & (1u << k)) continue;  // the reference would never return from this apply_action
-          leaf->children.push_back(tree.make(children[(size_t)i * CAAA_ACTIONS + k], actions[(size_t)i * CAAA_ACTIONS + k], leaf));
+          Node* child = tree.make(children[(size_t)i * CAAA_ACTIONS + k], actions[(size_t)i * CAAA_ACTIONS + k], leaf);
+          leaf->children.push_back(child);
+          if (k == picked[i]) target = child;
         }
       }
-      targets[i] = leaf->children.empty() ? leaf : leaf->children[rng() % leaf->children.size()];
-      states[i] = targets[i]->state;
-    }
-    // 3. rollouts_per_leaf playouts from every target in one launch
-    results.resize((size_t)nl * rollouts_per_leaf);
-    rc = caaa_gpu_rollout_batch(states.data(), nl, rollouts_per_leaf, seed, next_game_id, results.data(), nullptr, nullptr);
-    if (rc != CAAA_OK) return rc;
-    next_game_id += (uint64_t)nl * (uint64_t)rollouts_per_leaf;
-    // 4. clear the virtual visits and back-propagate
-    for (int i = 0; i < nl; i++) {
-      for (Node* n = leaves[i]; n != nullptr; n = n->parent) n->pending -= rollouts_per_leaf;
-      leaves[i]->in_batch = false;
-      double sum = 0.0;
-      for (int r = 0; r < rollouts_per_leaf; r++) sum += results[(size_t)i * rollouts_per_leaf + r];
-      backpropagate(targets[i], sum, rollouts_per_leaf);
+      for (Node* n = leaf; n != nullptr; n = n->parent) n->pending -= rollouts_per_leaf;
+      leaf->in_batch = false;
+      backpropagate(target, sums[i], rollouts_per_leaf);
     }
     done += nl;
     playouts += (int64_t)nl * rollouts_per_leaf;
+  }
+  if (depth > 1) caaa_gpu_set_rollout_sms(0);
+  if (rc != CAAA_OK) {
+    for (const Flight& f : flights) caaa_gpu_leaf_batch_collect(f.handle, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return rc;
   }
   std::memset(out, 0, sizeof(*out));
   out->n_children = (int32_t)std::min<size_t>(root->children.size(), CAAA_ACTIONS);
@@ -161,4 +191,12 @@ extern "C" int caaa_mcts_search(const CaaaGameState* root_state, int64_t iterati
   out->nodes = (int64_t)tree.pool.size();
   if (best_action) *best_action = best_a;
   return CAAA_OK;
+}
+
+// leaves_per_batch == 1 is the reference's sequential loop (every selection sees every earlier result); wider
+// batches keep two in flight.
+extern "C" int caaa_mcts_search(const CaaaGameState* root_state, int64_t iterations, int rollouts_per_leaf,
+                                int leaves_per_batch, uint64_t seed, CaaaRootStats* out, uint8_t* best_action) {
+  return caaa_mcts_search_pipelined(root_state, iterations, rollouts_per_leaf, leaves_per_batch, leaves_per_batch > 1 ? 2 : 1, seed, out,
+                                    best_action);
 }

@@ -79,6 +79,11 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
+// Orders this thread's pool / bitmap accesses at GPU scope (message passing between CTAs: data, fence, flag).
+// The pool is read and written with .cg accesses that bypass L1, so the acquire-release fence is enough;
+// __threadfence() (fence.sc + L1 invalidation) was 5 % of the kernel's stall samples in round 1.
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long ld_vol_u64(const unsigned long long* p) {
   return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
@@ -135,6 +140,53 @@ __device__ __noinline__ void restart_lanes(const RolloutArgs& a, Game* warp_game
       }
     }
   }
+}
+
+// One visit of `kind` for the lanes in `mask` (all of them call this together).  Returns PH_DONE / PH_YIELDED;
+// live = false, need_start = true when the game ended in this visit.
+template <bool STATS>
+__device__ __forceinline__ int run_kind(int kind, Game* g, const RunCtx cx, unsigned mask, int yield, const RolloutArgs& a, LaneTotals& tot,
+                                        bool& live, bool& need_start) {
+  int res = PH_DONE;
+  switch (kind) {
+    case CAAA_PH_MOVE_FIGHTERS: res = move_fighter_units<false>(g, cx, mask, yield); break;
+    case CAAA_PH_MOVE_BOMBERS: res = move_bomber_units<false>(g, cx, mask, yield); break;
+    case CAAA_PH_STAGE_TRANSPORTS: res = stage_transport_units<false>(g, cx, mask, yield); break;
+    // tanks, artillery and infantry are consecutive phases of one mover: one visit, one merged flat loop
+    // (queues 4 and 5 stay empty)
+    case CAAA_PH_MOVE_TANKS: res = move_land_units<false>(g, cx, mask, CAAA_PH_MOVE_TANKS, CAAA_PH_MOVE_INFANTRY, yield); break;
+    // ... and so are loaded transports, submarines and surface ships (queues 7 and 8 stay empty)
+    case CAAA_PH_MOVE_TRANSPORTS: res = move_sea_units<false>(g, cx, mask, yield); break;
+    case CAAA_PH_SEA_BATTLES: res = resolve_sea_battles<false>(g, cx, mask, yield); break;
+    case CAAA_PH_UNLOAD_TRANSPORTS: res = unload_transports<false>(g, cx, mask, yield); break;
+    case CAAA_PH_LAND_BATTLES: res = resolve_land_battles<false>(g, cx, mask, yield); break;
+    case CAAA_PH_MOVE_AA_GUNS: res = move_land_unit_type<false>(g, cx, mask, AA_GUNS, CAAA_PH_MOVE_AA_GUNS, yield); break;
+    case CAAA_PH_LAND_FIGHTERS: res = land_fighter_units<false>(g, cx, mask, yield); break;
+    case CAAA_PH_LAND_BOMBERS: res = land_bomber_units<false>(g, cx, mask, yield); break;
+    case Q_EOT: {  // reference src/engine.cpp:4229-4241
+      res = buy_units<false>(g, cx, mask, yield);
+      if (res != PH_YIELDED) {
+        crash_air_units(g, cx);
+        reset_units_fully(g);
+        collect_money(g, cx);
+        rotate_turns(g, cx);
+        g->turns++;
+        const double score = evaluate_state(g, cx);
+        if (!(score > 0.01 && score < 0.99 && g->turns < 1000)) {
+          const unsigned long long gi = ((unsigned long long)g->game_hi << 32 | g->game_lo) - a.first_game_id;
+          finish_playout<STATS>(g, score, gi, a, tot);
+          live = false;
+          need_start = true;
+        }
+      }
+      break;
+    }
+    default:  // Q_FREE: an empty pool entry
+      live = false;
+      need_start = true;
+      break;
+  }
+  return res;
 }
 
 // LANES = games per warp (16: 14 warps per SM).  A warp serves ONE kind of work at a time: it claims games waiting
@@ -240,7 +292,10 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         // the host reports the failure (it would mean a lost pool entry, i.e. a bug in this scheduler)
         if (*reinterpret_cast<volatile int*>(&GS->aborted)) break;
         if (clock64() - last_work > 8000000000LL) {
-          if (lane == 0) atomicExch(&GS->aborted, 1);
+          if (lane == 0) {
+            atomicExch(&GS->aborted, 1);
+            if (a.abort_flag != nullptr) atomicExch(a.abort_flag, 1);
+          }
           break;
         }
         __nanosleep(200);
@@ -267,7 +322,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         last_work = clock64();
         d_batches++;
         d_items += (unsigned)n_new;
-        __threadfence();
+        fence_gpu();
         // the j-th new entry goes to the j-th free lane
         const int my_rank = __popc(free_lanes & ((1u << lane) - 1u));
         const bool got = ((free_lanes >> lane) & 1u) && my_rank < n_new;
@@ -312,46 +367,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       const int yield = (pct > 0 && nh >= 6) ? (nh * pct + 99) / 100 : 0;
       int res = PH_DONE;
       bool live = runs, need_start = false;
-      if (runs) {
-        switch (kind) {
-          case CAAA_PH_MOVE_FIGHTERS: res = move_fighter_units<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_MOVE_BOMBERS: res = move_bomber_units<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_STAGE_TRANSPORTS: res = stage_transport_units<false>(g, cx, mhave, yield); break;
-          // tanks, artillery and infantry are consecutive phases of one mover: one visit, one merged flat loop
-          // (queues 4 and 5 stay empty)
-          case CAAA_PH_MOVE_TANKS: res = move_land_units<false>(g, cx, mhave, CAAA_PH_MOVE_TANKS, CAAA_PH_MOVE_INFANTRY, yield); break;
-          // ... and so are loaded transports, submarines and surface ships (queues 7 and 8 stay empty)
-          case CAAA_PH_MOVE_TRANSPORTS: res = move_sea_units<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_SEA_BATTLES: res = resolve_sea_battles<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_UNLOAD_TRANSPORTS: res = unload_transports<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_LAND_BATTLES: res = resolve_land_battles<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_MOVE_AA_GUNS: res = move_land_unit_type<false>(g, cx, mhave, AA_GUNS, CAAA_PH_MOVE_AA_GUNS, yield); break;
-          case CAAA_PH_LAND_FIGHTERS: res = land_fighter_units<false>(g, cx, mhave, yield); break;
-          case CAAA_PH_LAND_BOMBERS: res = land_bomber_units<false>(g, cx, mhave, yield); break;
-          case Q_EOT: {  // reference src/engine.cpp:4229-4241
-            res = buy_units<false>(g, cx, mhave, yield);
-            if (res != PH_YIELDED) {
-              crash_air_units(g, cx);
-              reset_units_fully(g);
-              collect_money(g, cx);
-              rotate_turns(g, cx);
-              g->turns++;
-              const double score = evaluate_state(g, cx);
-              if (!(score > 0.01 && score < 0.99 && g->turns < 1000)) {
-                const unsigned long long gi = ((unsigned long long)g->game_hi << 32 | g->game_lo) - a.first_game_id;
-                finish_playout<STATS>(g, score, gi, a, tot);
-                live = false;
-                need_start = true;
-              }
-            }
-            break;
-          }
-          default:  // Q_FREE: an empty pool entry
-            live = false;
-            need_start = true;
-            break;
-        }
-      }
+      if (runs) res = run_kind<STATS>(kind, g, cx, mhave, yield, a, tot, live, need_start);
       __syncwarp();
       if (dbg != nullptr && lane == 0) {
         atomicAdd(&dbg->kind_cycles[kind], (unsigned long long)(clock64() - d_c0));
@@ -388,7 +404,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         for (int k = 0; k < KW; k++)
           if (k * 32 + lane < GAME_WORDS) __stcg(dst + k * 32 + lane, src[k * 32 + lane]);
       }
-      __threadfence();
+      fence_gpu();
       __syncwarp();
       {
         const unsigned peers = __match_any_sync(FULL, nxt);

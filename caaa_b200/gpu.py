@@ -11,8 +11,14 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcaaa_gpu
 # every symbol include/caaa_gpu.h declares
 SYMBOLS = ["caaa_gpu_init", "caaa_gpu_shutdown", "caaa_gpu_last_error", "caaa_gpu_get_tables",
            "caaa_gpu_device_info", "caaa_gpu_rollout_batch", "caaa_gpu_rollout_batch_device",
-           "caaa_gpu_set_stream", "caaa_gpu_random_play_until_terminal", "caaa_gpu_advance",
-           "caaa_gpu_resolve_battles", "caaa_gpu_expand", "caaa_gpu_evaluate"]
+           "caaa_gpu_synchronize", "caaa_gpu_set_stream", "caaa_gpu_random_play_until_terminal", "caaa_gpu_advance",
+           "caaa_gpu_resolve_battles", "caaa_gpu_resolve_battles_device", "caaa_gpu_expand", "caaa_gpu_evaluate",
+           "caaa_gpu_leaf_batch_submit", "caaa_gpu_leaf_batch_collect", "caaa_gpu_set_rollout_sms"]
+
+
+# the root-parallel exchange step (NCCL, bound at run time)
+ROOT_SYMBOLS = ["caaa_root_allreduce", "caaa_root_unique_id", "caaa_root_comm_init", "caaa_root_allreduce_host",
+                "caaa_root_comm_destroy", "caaa_root_last_error"]
 
 
 class CaaaGpuError(RuntimeError):
@@ -36,8 +42,17 @@ def load_library(path=LIB_PATH):
     lib.caaa_gpu_random_play_until_terminal.restype = C.c_double
     lib.caaa_gpu_advance.argtypes = [vp, i32, u64, u64, i32, vp, vp, vp]
     lib.caaa_gpu_resolve_battles.argtypes = [vp, i32, u64, u64, vp, vp, vp]
+    lib.caaa_gpu_resolve_battles_device.argtypes = [vp, i32, u64, u64, vp, vp, vp, vp]
     lib.caaa_gpu_expand.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.caaa_gpu_evaluate.argtypes = [vp, i32, vp]
+    lib.caaa_gpu_leaf_batch_submit.argtypes = [i32, vp, i32, i32, u64, u64, vp]
+    lib.caaa_gpu_leaf_batch_collect.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.caaa_gpu_set_rollout_sms.argtypes = [i32]
+    lib.caaa_root_allreduce.argtypes = [vp, i32, vp, vp, vp]
+    lib.caaa_root_unique_id.argtypes = [vp]
+    lib.caaa_root_comm_init.argtypes = [vp, i32, i32]
+    lib.caaa_root_allreduce_host.argtypes = [i32, vp, vp, vp]
+    lib.caaa_root_last_error.restype = C.c_char_p
     return lib
 
 
@@ -90,6 +105,9 @@ class GpuEngine:
                                                            int(seed), int(first_game_id), d_results_ptr,
                                                            d_stats_ptr, d_summary_ptr, stream_ptr))
 
+    def synchronize(self):
+        self._check(self.lib.caaa_gpu_synchronize())
+
     def set_stream(self, seed, next_game_id=0):
         self._check(self.lib.caaa_gpu_set_stream(int(seed), int(next_game_id)))
 
@@ -117,6 +135,12 @@ class GpuEngine:
                                                       out.ctypes.data, draws.ctypes.data, summary.ctypes.data))
         return out, draws, summary[0]
 
+    def resolve_battles_device(self, d_states_ptr, n, seed, first_game_id, d_out_ptr=None, d_draws_ptr=None, d_summary_ptr=None,
+                               stream_ptr=None):
+        """Raw device addresses (ints), asynchronous on the stream; d_summary is accumulated into."""
+        self._check(self.lib.caaa_gpu_resolve_battles_device(d_states_ptr, int(n), int(seed), int(first_game_id), d_out_ptr,
+                                                             d_draws_ptr, d_summary_ptr, stream_ptr))
+
     def expand(self, leaves, want_children=True):
         leaves = _states(leaves)
         n = leaves.shape[0]
@@ -127,6 +151,28 @@ class GpuEngine:
         self._check(self.lib.caaa_gpu_expand(leaves.ctypes.data, n, n_actions.ctypes.data, actions.ctypes.data,
                                              children.ctypes.data if want_children else None, status.ctypes.data))
         return n_actions, actions, children, status
+
+    def leaf_batch_submit(self, handle, leaves, rollouts_per_leaf, seed, first_game_id, child_pick):
+        leaves = _states(leaves)
+        pick = np.ascontiguousarray(child_pick, dtype=np.uint64)
+        assert len(pick) == leaves.shape[0]
+        self._check(self.lib.caaa_gpu_leaf_batch_submit(int(handle), leaves.ctypes.data, leaves.shape[0], int(rollouts_per_leaf),
+                                                        int(seed), int(first_game_id), pick.ctypes.data))
+        return leaves.shape[0]
+
+    def leaf_batch_collect(self, handle, n):
+        out = {"scores": np.zeros(n), "n_actions": np.zeros(n, np.uint8), "actions": np.zeros((n, 20), np.uint8),
+               "children": np.zeros((n, 20, STATE_BYTES), np.uint8), "status": np.zeros(n, np.uint32),
+               "picked": np.zeros(n, np.int32), "sums": np.zeros(n), "summary": np.zeros(1, dtype=SUMMARY_DTYPE)}
+        self._check(self.lib.caaa_gpu_leaf_batch_collect(int(handle), out["scores"].ctypes.data, out["n_actions"].ctypes.data,
+                                                         out["actions"].ctypes.data, out["children"].ctypes.data,
+                                                         out["status"].ctypes.data, out["picked"].ctypes.data,
+                                                         out["sums"].ctypes.data, out["summary"].ctypes.data))
+        out["summary"] = out["summary"][0]
+        return out
+
+    def set_rollout_sms(self, sms):
+        self._check(self.lib.caaa_gpu_set_rollout_sms(int(sms)))
 
     def evaluate(self, states):
         states = _states(states)

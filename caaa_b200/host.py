@@ -7,7 +7,7 @@ from . import gpu
 from .layout import STATE_BYTES
 
 SYMBOLS = ["caaa_state_from_json_file", "caaa_state_from_json_text", "caaa_state_to_json_text",
-           "caaa_state_to_json_file", "caaa_mcts_search"]
+           "caaa_state_to_json_file", "caaa_mcts_search", "caaa_mcts_search_pipelined"]
 
 
 class RootStats(C.Structure):
@@ -22,6 +22,7 @@ def _lib():
     lib.caaa_state_to_json_text.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     lib.caaa_state_to_json_file.argtypes = [C.c_char_p, C.c_void_p]
     lib.caaa_mcts_search.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.caaa_mcts_search_pipelined.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -51,13 +52,18 @@ def state_to_json(state):
     return buf.value.decode()
 
 
-def mcts_search(engine, state, iterations, rollouts_per_leaf=1, leaves_per_batch=1, seed=0):
-    """caaa_mcts_search on an initialised GpuEngine; returns (actions, visits, values, best_action, info)."""
+def mcts_search(engine, state, iterations, rollouts_per_leaf=1, leaves_per_batch=1, seed=0, depth=None):
+    """caaa_mcts_search (depth=None) / caaa_mcts_search_pipelined on an initialised GpuEngine;
+    returns (actions, visits, values, best_action, info)."""
     state = np.ascontiguousarray(state, dtype=np.uint8)
     out = RootStats()
     best = C.c_uint8(255)
-    engine._check(_lib().caaa_mcts_search(state.ctypes.data, int(iterations), int(rollouts_per_leaf), int(leaves_per_batch),
-                                          int(seed), C.byref(out), C.byref(best)))
+    if depth is None:
+        engine._check(_lib().caaa_mcts_search(state.ctypes.data, int(iterations), int(rollouts_per_leaf), int(leaves_per_batch),
+                                              int(seed), C.byref(out), C.byref(best)))
+    else:
+        engine._check(_lib().caaa_mcts_search_pipelined(state.ctypes.data, int(iterations), int(rollouts_per_leaf),
+                                                        int(leaves_per_batch), int(depth), int(seed), C.byref(out), C.byref(best)))
     n = out.n_children
     info = {"iterations": out.iterations, "playouts": out.playouts, "nodes": out.nodes}
     return (np.array(out.actions[:n], dtype=np.uint8), np.array(out.visits[:n], dtype=np.int64),

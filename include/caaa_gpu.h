@@ -27,6 +27,7 @@ extern "C" {
 #define CAAA_E_CUDA (-2)
 #define CAAA_E_ARG (-3)
 #define CAAA_E_NOT_INIT (-4)
+#define CAAA_E_BUSY (-5) /* another thread is inside the library: the context serves one caller at a time */
 
 /* Whole-batch counters, accumulated on the device by the rollout kernel. */
 typedef struct CaaaBatchSummary {
@@ -59,10 +60,17 @@ int caaa_gpu_rollout_batch(const CaaaGameState* states, int n_states, int rollou
 
 /* Same, with every buffer already resident in device memory (device pointers; stats/summary may be
  * NULL) and asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).  d_summary must be
- * zeroed by the caller; kernel_ms is not filled in. */
+ * zeroed by the caller; kernel_ms is not filled in.  d_summary->playouts == n_states * rollouts_per_state once
+ * the stream has drained says the batch is complete; caaa_gpu_synchronize() reports a watchdog abort. */
 int caaa_gpu_rollout_batch_device(const void* d_states, int n_states, int rollouts_per_state, uint64_t seed,
                                   uint64_t first_game_id, double* d_results, CaaaRolloutStats* d_stats,
                                   CaaaBatchSummary* d_summary, void* cuda_stream);
+
+/* Waits for every asynchronous launch issued through the *_device entry points and reports what they could not:
+ * CAAA_E_CUDA if a kernel's watchdog stopped a batch (caaa_gpu_last_error() says so).  Up to three device
+ * launches may be in flight at a time, on the same or on different streams; each owns its own scratch, and a
+ * fourth launch waits on the device for the first to drain. */
+int caaa_gpu_synchronize(void);
 
 /* Single-state shim with the reference's signature semantics (include/engine.h:158): one playout
  * from *state with the next game id of an internal counter (caaa_gpu_set_stream sets seed and
@@ -83,6 +91,11 @@ int caaa_gpu_advance(const CaaaGameState* states, int n, uint64_t seed, uint64_t
 int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, uint64_t first_game_id,
                              CaaaGameState* out_states, int32_t* out_draws, CaaaBatchSummary* summary);
 
+/* Same, with every buffer already resident in device memory (16-byte aligned device pointers; outputs and
+ * d_summary may be NULL; d_summary is accumulated into, not zeroed) and asynchronous on `cuda_stream`. */
+int caaa_gpu_resolve_battles_device(const void* d_states, int n, uint64_t seed, uint64_t first_game_id, void* d_out_states,
+                                    int32_t* d_out_draws, CaaaBatchSummary* d_summary, void* cuda_stream);
+
 /* Tree expansion (reference get_possible_actions + apply_action per action, include/engine.h:153-154,
  * src/engine.cpp:4050-4183; what expand_node does, src/mcts.cpp:110-126): for each leaf the action
  * list (n_actions[i] <= 20, actions[i*20 ..]) and, if children != NULL, the state reached by every
@@ -92,9 +105,41 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
 int caaa_gpu_expand(const CaaaGameState* leaves, int n, uint8_t* n_actions, uint8_t* actions,
                     CaaaGameState* children, uint32_t* status);
 
+/* ---- Asynchronous leaf batches: one MCTS iteration's device work for n leaves at once (reference src/mcts.cpp:78-94:
+ * is_terminal_state, expand_node, `rand() % num_children`, random_play_until_terminal), without a host round trip
+ * between the steps.  submit() enqueues, on the handle's own stream: terminal test -> action lists -> all children ->
+ * the child to roll out (child_pick[i] % number of playable children; terminal / childless leaves roll out from
+ * themselves) -> rollouts_per_leaf playouts from each picked child (game ids first_game_id + i * rollouts_per_leaf + r)
+ * -> per-leaf sums of the results in a fixed order.  The children stay on the device for the rollout; collect() waits
+ * and returns what the host tree needs: scores, action lists, children, status (as caaa_gpu_expand), picked[i] (index
+ * into leaf i's action list, -1 = the leaf itself) and sum_results[i].  Handles 0..2 are independent: a search keeps
+ * two or three batches in flight.  Any output pointer may be NULL. */
+int caaa_gpu_leaf_batch_submit(int handle, const CaaaGameState* leaves, int n, int rollouts_per_leaf, uint64_t seed,
+                               uint64_t first_game_id, const uint64_t* child_pick);
+int caaa_gpu_leaf_batch_collect(int handle, double* scores, uint8_t* n_actions, uint8_t* actions, CaaaGameState* children,
+                                uint32_t* status, int32_t* picked, double* sum_results, CaaaBatchSummary* summary);
+/* SMs a rollout launch may occupy (0 = all).  The persistent rollout kernel otherwise holds every SM until its batch
+ * has drained; a pipelined search leaves a few SMs free so that the next batch's short expansion kernels run beside it. */
+int caaa_gpu_set_rollout_sms(int sms);
+
 /* is_terminal_state / evaluate_state on caller-supplied states, with the unit totals taken from
  * the states themselves (the reference reads stale globals here, src/engine.cpp:4244-4248,4314). */
 int caaa_gpu_evaluate(const CaaaGameState* states, int n, double* scores);
+
+/* ---- Root-parallel MCTS (BASELINE config 5): the one exchange step.  Every rank searches its own tree
+ * (reference src/mcts.cpp:65-108 per rank, seed = base + rank); the root children's {visits, value} are then summed
+ * over the ranks with ncclAllReduce over NVLink / NVSwitch.  Root actions are in the same order on every rank because
+ * get_possible_actions is deterministic.  NCCL is bound at run time (dlopen), not at load time. */
+/* `nccl_comm` is the caller's ncclComm_t; device pointers, in place, asynchronous on `cuda_stream`; both reductions
+ * are one NCCL group. */
+int caaa_root_allreduce(void* nccl_comm, int n_children, int64_t* d_visits, double* d_values, void* cuda_stream);
+/* The library's own communicator, for hosts that have none: rank 0 makes the 128-byte id, every rank (one per GPU,
+ * after cudaSetDevice / caaa_gpu_init) joins with it, then sums host buffers in place. */
+int caaa_root_unique_id(uint8_t id128[128]);
+int caaa_root_comm_init(const uint8_t id128[128], int rank, int world);
+int caaa_root_allreduce_host(int n_children, int64_t* visits, double* values, double* elapsed_us);
+int caaa_root_comm_destroy(void);
+const char* caaa_root_last_error(void);
 
 #ifdef __cplusplus
 }

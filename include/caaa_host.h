@@ -42,6 +42,10 @@ typedef struct CaaaRootStats {
  * Needs caaa_gpu_init().  best_action may be NULL. */
 int caaa_mcts_search(const CaaaGameState* root_state, int64_t iterations, int rollouts_per_leaf,
                      int leaves_per_batch, uint64_t seed, CaaaRootStats* out, uint8_t* best_action);
+/* Same with an explicit pipeline depth (1..3 leaf batches in flight; caaa_mcts_search uses 1 for leaves_per_batch == 1,
+ * else 2).  Selection for batch k+1 runs while batch k is on the device, with virtual visits for its pending results. */
+int caaa_mcts_search_pipelined(const CaaaGameState* root_state, int64_t iterations, int rollouts_per_leaf,
+                               int leaves_per_batch, int depth, uint64_t seed, CaaaRootStats* out, uint8_t* best_action);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,9 @@ def test_header_symbols_exported():
     header2 = open(os.path.join(ROOT, "include", "caaa_host.h")).read()
     declared2 = sorted(set(re.findall(r"\b(caaa_(?:state|mcts)_\w+)\s*\(", header2)))
     assert declared2 == sorted(host.SYMBOLS)
-    for name in declared + declared2:
+    declared3 = sorted(set(re.findall(r"\b(caaa_root_\w+)\s*\(", header)))
+    assert declared3 == sorted(gpu.ROOT_SYMBOLS)
+    for name in declared + declared2 + declared3:
         assert hasattr(lib, name), name
     # the reference-named C++ entry points of caaa_engine_compat.h (Itanium-mangled)
     for name in ("_Z20initialize_constantsv", "_Z14load_game_dataPKc", "_Z19get_game_state_copyv",

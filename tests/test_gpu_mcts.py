@@ -1,0 +1,93 @@
+"""GPU tier (-m gpu): the asynchronous leaf-batch entry points, the pipelined search and root-parallel MCTS."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from caaa_b200 import layout
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from caaa_b200 import gpu
+    return gpu.GpuEngine(0)
+
+
+def device_order_sum(r):
+    """reduce_results_kernel's fixed order: 32 lane-strided sequential sums, then a shuffle tree."""
+    acc = np.zeros(64)
+    for lane in range(32):
+        part = r[lane::32]
+        acc[lane] = np.add.accumulate(part)[-1] if len(part) else 0.0
+    for o in (16, 8, 4, 2, 1):
+        acc[:32] = acc[:32] + acc[o:o + 32]
+    return acc[0]
+
+
+def test_leaf_batch_matches_the_separate_calls(eng):
+    """One submit/collect == evaluate + expand + (pick % playable children) + rollout_batch + per-leaf sum."""
+    a = np.load(os.path.join(GOLD, "advance.npz"))
+    leaves = np.concatenate([layout.start_state().reshape(1, -1), a["states"][:70]])
+    n, per, seed, first = len(leaves), 96, 0x7EAF, 123_000
+    pick = np.random.default_rng(5).integers(0, 1 << 62, n).astype(np.uint64)
+    eng.leaf_batch_submit(1, leaves, per, seed, first, pick)
+    got = eng.leaf_batch_collect(1, n)
+    scores = eng.evaluate(leaves)
+    n_actions, actions, children, status = eng.expand(leaves)
+    assert np.array_equal(got["scores"], scores) and np.array_equal(got["n_actions"], n_actions)
+    assert np.array_equal(got["status"], status)
+    targets = leaves.copy()
+    for i in range(n):
+        k = int(n_actions[i])
+        assert np.array_equal(got["actions"][i][:k], actions[i][:k])
+        assert np.array_equal(got["children"][i][:k], children[i][:k])
+        terminal = scores[i] > 0.99 or scores[i] < 0.01
+        playable = [j for j in range(k) if not (int(status[i]) >> j) & 1]
+        want = -1
+        if not terminal and not (int(status[i]) & 0x80000000) and playable:
+            want = playable[int(pick[i]) % len(playable)]
+            targets[i] = children[i][want]
+        assert got["picked"][i] == want, i
+    res, _, summ = eng.rollout_batch(targets, per, seed, first)
+    for i in range(n):
+        assert got["sums"][i] == device_order_sum(res[i * per:(i + 1) * per]), i
+    assert got["summary"]["playouts"] == n * per and got["summary"]["plies"] == summ["plies"]
+
+
+def test_pipelined_search_is_deterministic_and_complete(eng):
+    from caaa_b200 import host
+    s0 = layout.start_state()
+    runs = []
+    for depth in (1, 2, 3, 2):
+        a, v, x, best, info = host.mcts_search(eng, s0, 600, rollouts_per_leaf=128, leaves_per_batch=32, seed=9, depth=depth)
+        assert a.tolist() == [6, 5, 4, 3, 2, 0]              # root expansion, SURVEY.md Appendix E
+        assert v.sum() == 600 * 128 and info["playouts"] == 600 * 128 and info["iterations"] == 600
+        assert (x >= 0).all() and (x <= v).all() and best in a.tolist()
+        runs.append((v, x, best))
+    assert np.array_equal(runs[1][0], runs[3][0]) and np.array_equal(runs[1][1], runs[3][1])  # same depth, same seed -> same tree
+    # depth 1 with one leaf per batch is the reference's sequential loop: every selection sees every earlier result
+    a, v, x, best, info = host.mcts_search(eng, s0, 400, 1, 1, seed=3)
+    assert v.sum() == 400 and info["nodes"] > 400
+
+
+def test_root_parallel_two_ranks_real_search(tmp_path):
+    """BASELINE config 5 at world size 2 with the REAL search on two GPUs: the statistics all-reduced by
+    caaa_root_allreduce (NCCL) equal the host-side sum of the per-rank statistics."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29631", os.path.join(ROOT, "tools", "root_parallel_check.py"), "--iterations", "96", "--rollouts", "256",
+           "--leaves-per-batch", "32"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["allreduced_equals_host_sum"] and line["n_gpus"] == 2
+    assert sum(line["root_visits"]) == 2 * 96 * 256

@@ -48,12 +48,15 @@ def _rank_main(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
 
-    def fake_search(state, iterations, seed):  # stands in for the per-GPU tree search
+    # CPU tier: there is no GPU here, so no search can run (the library has no CPU path).  This test covers the exchange
+    # plumbing only -- seed = base + rank, action-list agreement, sum over ranks -- on synthetic per-rank statistics;
+    # the REAL search on two GPUs with the NCCL C entry point is tests/test_gpu_mcts.py::test_root_parallel_two_ranks_real_search.
+    def synthetic_rank_stats(state, iterations, seed):
         rng = np.random.default_rng(seed)
         visits = rng.integers(1, 1000, 6)
         return np.array([6, 5, 4, 3, 2, 0]), visits, visits * rng.random(6)
 
-    a, v, x, best = root_parallel.root_parallel_search(fake_search, None, 100, 1000)
+    a, v, x, best = root_parallel.root_parallel_search(synthetic_rank_stats, None, 100, 1000)
     if rank == 0:
         torch.save({"a": a, "v": v, "x": x, "best": best}, out)
     dist.destroy_process_group()
