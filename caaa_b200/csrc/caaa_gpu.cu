@@ -19,6 +19,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "../../include/caaa_gpu.h"
 #include "engine2.cuh"
@@ -337,6 +338,43 @@ __global__ void __launch_bounds__(SMALL_THREADS) evaluate_kernel(const DevTables
   scores[i] = evaluate_state(g, cx);
 }
 
+// ---- AoS <-> SoA (north_star: "structure-of-arrays batch in HBM with coalesced 128-bit loads and stores") ----
+// SoA form of a batch of n states: 42 chunks of 16 bytes per state (670 bytes + 2 zero pad bytes), CHUNK-MAJOR:
+// chunk c of state i lives at soa[(c * n_pad + i) * 16], n_pad = n rounded up to 32.  A warp that reads chunk c of 32
+// consecutive states issues one LDG.128 per lane = 512 contiguous bytes.  One CTA converts a tile of 32 states through
+// shared memory so that both sides are coalesced.  (Where this layout pays and where it does not: DESIGN.md section 3.)
+constexpr int SOA_CHUNKS = (CAAA_STATE_BYTES + 15) / 16;  // 42
+__global__ void __launch_bounds__(128) pack_kernel(const uint8_t* aos, int n, int n_pad, uint4* soa) {
+  __shared__ __align__(16) uint8_t tile[32 * SOA_CHUNKS * 16];
+  const int base = blockIdx.x * 32, cnt = n - base < 32 ? n - base : 32;
+  for (int i = threadIdx.x; i < 32 * SOA_CHUNKS * 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tile)[i] = 0u;
+  __syncthreads();
+  const uint16_t* s16 = reinterpret_cast<const uint16_t*>(aos + (size_t)base * CAAA_STATE_BYTES);  // records are 2-byte aligned
+  for (int h = threadIdx.x; h < cnt * (CAAA_STATE_BYTES / 2); h += blockDim.x) {
+    const int g = h / (CAAA_STATE_BYTES / 2), o = h % (CAAA_STATE_BYTES / 2);
+    reinterpret_cast<uint16_t*>(tile + g * SOA_CHUNKS * 16)[o] = s16[h];
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < SOA_CHUNKS * 32; k += blockDim.x) {
+    const int c = k / 32, g = k % 32;
+    if (base + g < n_pad) soa[(size_t)c * n_pad + base + g] = reinterpret_cast<const uint4*>(tile + g * SOA_CHUNKS * 16)[c];
+  }
+}
+__global__ void __launch_bounds__(128) unpack_kernel(const uint4* soa, int n, int n_pad, uint8_t* aos) {
+  __shared__ __align__(16) uint8_t tile[32 * SOA_CHUNKS * 16];
+  const int base = blockIdx.x * 32, cnt = n - base < 32 ? n - base : 32;
+  for (int k = threadIdx.x; k < SOA_CHUNKS * 32; k += blockDim.x) {
+    const int c = k / 32, g = k % 32;
+    if (g < cnt) reinterpret_cast<uint4*>(tile + g * SOA_CHUNKS * 16)[c] = soa[(size_t)c * n_pad + base + g];
+  }
+  __syncthreads();
+  uint16_t* d16 = reinterpret_cast<uint16_t*>(aos + (size_t)base * CAAA_STATE_BYTES);
+  for (int h = threadIdx.x; h < cnt * (CAAA_STATE_BYTES / 2); h += blockDim.x) {
+    const int g = h / (CAAA_STATE_BYTES / 2), o = h % (CAAA_STATE_BYTES / 2);
+    d16[h] = reinterpret_cast<const uint16_t*>(tile + g * SOA_CHUNKS * 16)[o];
+  }
+}
+
 // Leaf batches (MCTS): the child each visited leaf rolls out, chosen on the device so that the expansion's children
 // never leave it before the rollout (reference src/mcts.cpp:84-94: expand, `rand() % num_children`, rollout).
 // Terminal leaves and leaves without a playable child roll out from themselves (picked = -1).
@@ -431,6 +469,8 @@ struct LeafBatch {
 struct Context {
   bool ready = false;
   BattlePipe battle;
+  unsigned int* d_battle_counters = nullptr;  // work counters of the battle kernel: one per pipeline buffer + four for device launches
+  unsigned next_battle_counter = 0;
   LeafBatch leaf[N_LEAF_BATCHES];
   int rollout_sms = 0;  // SMs a rollout launch may occupy (0 = all): a search leaves a few free for the next batch's expansion
   int device = -1;
@@ -658,9 +698,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     else                                                                                                                            \
       rollout_kernel_stream<false, NL><<<grid, STREAM_SLOTS / NL * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
   } while (0)
-    if (c.lanes == 32) CAAA_LAUNCH_STREAM(32);
-    else if (c.lanes == 8) CAAA_LAUNCH_STREAM(8);
-    else CAAA_LAUNCH_STREAM(16);
+    CAAA_LAUNCH_STREAM(16);  // (8 and 32 games per warp were measured: 0.91 M and 1.23 M playouts/s against 1.30 M)
     if (d_dbg != nullptr) {
       StreamDbg h;
       cudaStreamSynchronize(stream);
@@ -719,6 +757,7 @@ int caaa_gpu_init(int device) {
     CUDA_TRY(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
   }
   CUDA_TRY(cudaMalloc(&c.d_summary, sizeof(CaaaBatchSummary)));
+  CUDA_TRY(cudaMalloc(&c.d_battle_counters, (BattlePipe::NBUF + 4) * sizeof(unsigned int)));
   CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreate(&c.ev0));
   CUDA_TRY(cudaEventCreate(&c.ev1));
@@ -735,18 +774,14 @@ int caaa_gpu_init(int device) {
   if (c.pool_mult < 1) c.pool_mult = 1;
   if (c.pool_mult > MAX_POOL_MULT) c.pool_mult = MAX_POOL_MULT;
   const char* ln = std::getenv("CAAA_LANES");
-  c.lanes = ln ? std::atoi(ln) : 16;
-  if (c.lanes != 8 && c.lanes != 32) c.lanes = 16;
+  (void)ln;
+  c.lanes = 16;
   const char* gs = std::getenv("CAAA_GROUP");
   c.group_size = gs ? std::atoi(gs) : 16;
   if (c.group_size < 1) c.group_size = 1;
   if (c.group_size > MAX_GROUP) c.group_size = MAX_GROUP;
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));
@@ -781,6 +816,8 @@ int caaa_gpu_shutdown(void) {
     cudaEventDestroy(l.done);
   }
   cudaFree(c.d_summary);
+  cudaFree(c.d_battle_counters);
+  c.d_battle_counters = nullptr;
   for (LeafBatch& b : c.leaf) {
     if (!b.ready) continue;
     cudaStreamSynchronize(b.stream);
@@ -940,14 +977,40 @@ int caaa_gpu_advance(const CaaaGameState* states, int n, uint64_t seed, uint64_t
   return CAAA_OK;
 }
 
-static void launch_battles(const void* d_states, int n, uint64_t seed, uint64_t first_game_id, void* d_out, int32_t* d_draws,
-                           CaaaBatchSummary* d_summary, cudaStream_t stream) {
+// memcpy of a large block split over a few threads: one core moves ~8 GB/s between pageable and pinned memory, which
+// is less than half of what the PCIe link carries in each direction
+static void parallel_memcpy(void* dst, const void* src, size_t bytes, int threads) {
+  if (threads <= 1 || bytes < (size_t)(8u << 20)) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const size_t per = (bytes / (size_t)threads + 4095) / 4096 * 4096;
+  for (int k = 1; k < threads; k++) {
+    const size_t lo = (size_t)k * per;
+    if (lo >= bytes) break;
+    const size_t cnt = std::min(per, bytes - lo);
+    pool.emplace_back([=] { std::memcpy((uint8_t*)dst + lo, (const uint8_t*)src + lo, cnt); });
+  }
+  std::memcpy(dst, src, std::min(per, bytes));
+  for (std::thread& th : pool) th.join();
+}
+
+static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t first_game_id, void* d_out, int32_t* d_draws,
+                          CaaaBatchSummary* d_summary, unsigned int* d_counter, cudaStream_t stream) {
   Context& c = g_ctx;
-  const int tiles = (n + TILE_STATES - 1) / TILE_STATES;
-  int grid = (tiles + BATTLE_WARPS - 1) / BATTLE_WARPS;
-  if (grid > c.sm_count * 8) grid = c.sm_count * 8;  // warps loop over tiles; a multiple of the SM count
+  // every warp takes `run` consecutive states at a time from a device-wide counter: long enough for coalesced refills,
+  // short enough that the 148 x 6 warps finish together
+  int run = n / (c.sm_count * BATTLE_WARPS * 8);
+  run = run < 32 ? 32 : run > 1024 ? 1024 : run / 8 * 8;
+  const int want = (n + run - 1) / run;  // warps that can get a run at all
+  int grid = (want + BATTLE_WARPS - 1) / BATTLE_WARPS;
+  if (grid > c.sm_count) grid = c.sm_count;
+  CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
   battle_kernel<<<grid, BATTLE_WARPS * 32, BATTLE_SMEM, stream>>>(c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id,
-                                                                  (uint8_t*)d_out, d_draws, d_summary);
+                                                                  (uint8_t*)d_out, d_draws, d_summary, d_counter, run);
+  CUDA_TRY(cudaGetLastError());
+  return CAAA_OK;
 }
 
 int caaa_gpu_resolve_battles_device(const void* d_states, int n, uint64_t seed, uint64_t first_game_id, void* d_out_states,
@@ -955,9 +1018,9 @@ int caaa_gpu_resolve_battles_device(const void* d_states, int n, uint64_t seed, 
   CAAA_ENTER();
   if (!g_ctx.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
   if (!d_states || n <= 0) return fail(CAAA_E_ARG, "bad battle arguments");
-  launch_battles(d_states, n, seed, first_game_id, d_out_states, d_out_draws, d_summary, (cudaStream_t)cuda_stream);
-  CUDA_TRY(cudaGetLastError());
-  return CAAA_OK;
+  Context& c = g_ctx;
+  unsigned int* counter = c.d_battle_counters + BattlePipe::NBUF + (c.next_battle_counter++ % 4);  // up to four device launches in flight
+  return launch_battles(d_states, n, seed, first_game_id, d_out_states, d_out_draws, d_summary, counter, (cudaStream_t)cuda_stream);
 }
 
 // Host-buffer form: chunks of BATTLE_CHUNK states flow through three pinned staging buffers and three streams, so the
@@ -989,6 +1052,8 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
   CUDA_TRY(cudaMemsetAsync(c.d_summary, 0, sizeof(CaaaBatchSummary), c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   const int n_chunks = (int)(((size_t)n + chunk - 1) / chunk);
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int copy_threads = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;  // per direction
   std::mutex mu;
   std::condition_variable cv;
   int issued = 0, drained = 0;
@@ -999,7 +1064,7 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
     const int b = k % BattlePipe::NBUF;
     const size_t lo = (size_t)k * chunk, cnt = std::min(chunk, (size_t)n - lo);
     if (cudaEventSynchronize(bp.done[b]) != cudaSuccess) return false;
-    if (out_states) std::memcpy((uint8_t*)out_states + lo * CAAA_STATE_BYTES, bp.h_out[b], cnt * CAAA_STATE_BYTES);
+    if (out_states) parallel_memcpy((uint8_t*)out_states + lo * CAAA_STATE_BYTES, bp.h_out[b], cnt * CAAA_STATE_BYTES, copy_threads);
     if (out_draws) std::memcpy(out_draws + lo, bp.h_draws[b], cnt * sizeof(int32_t));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, bp.k0[b], bp.k1[b]) == cudaSuccess) kernel_ms += ms;
@@ -1032,14 +1097,13 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
       cv.wait(lk, [&] { return drained > k - BattlePipe::NBUF || failed; });
       if (failed) break;
     }
-    std::memcpy(bp.h_in[b], (const uint8_t*)states + lo * CAAA_STATE_BYTES, cnt * CAAA_STATE_BYTES);
+    parallel_memcpy(bp.h_in[b], (const uint8_t*)states + lo * CAAA_STATE_BYTES, cnt * CAAA_STATE_BYTES, copy_threads);
     cudaStream_t st = bp.stream[b];
     cudaError_t e = cudaMemcpyAsync(bp.d_in[b], bp.h_in[b], cnt * CAAA_STATE_BYTES, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaEventRecord(bp.k0[b], st);
-    if (e == cudaSuccess) {
-      launch_battles(bp.d_in[b], (int)cnt, seed, first_game_id + lo, out_states ? bp.d_out[b] : nullptr, bp.d_draws[b], c.d_summary, st);
-      e = cudaGetLastError();
-    }
+    if (e == cudaSuccess && launch_battles(bp.d_in[b], (int)cnt, seed, first_game_id + lo, out_states ? bp.d_out[b] : nullptr, bp.d_draws[b],
+                                           c.d_summary, c.d_battle_counters + b, st) != CAAA_OK)
+      e = cudaErrorLaunchFailure;
     if (e == cudaSuccess) e = cudaEventRecord(bp.k1[b], st);
     if (e == cudaSuccess && out_states) e = cudaMemcpyAsync(bp.h_out[b], bp.d_out[b], cnt * CAAA_STATE_BYTES, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && out_draws) e = cudaMemcpyAsync(bp.h_draws[b], bp.d_draws[b], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
@@ -1121,6 +1185,29 @@ int caaa_gpu_evaluate(const CaaaGameState* states, int n, double* scores) {
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(scores, c.d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   CUDA_TRY(cudaStreamSynchronize(c.stream));
+  return CAAA_OK;
+}
+
+// AoS <-> SoA on device-resident batches (device pointers, asynchronous on `cuda_stream`).
+int caaa_gpu_soa_bytes(int n, size_t* bytes) {
+  if (n <= 0 || !bytes) return fail(CAAA_E_ARG, "bad arguments");
+  *bytes = (size_t)SOA_CHUNKS * (size_t)((n + 31) / 32 * 32) * 16;
+  return CAAA_OK;
+}
+int caaa_gpu_pack(const void* d_states_aos, int n, void* d_states_soa, void* cuda_stream) {
+  CAAA_ENTER();
+  if (!g_ctx.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
+  if (!d_states_aos || !d_states_soa || n <= 0 || (reinterpret_cast<uintptr_t>(d_states_soa) & 15u)) return fail(CAAA_E_ARG, "bad pack arguments");
+  pack_kernel<<<(n + 31) / 32, 128, 0, (cudaStream_t)cuda_stream>>>((const uint8_t*)d_states_aos, n, (n + 31) / 32 * 32, (uint4*)d_states_soa);
+  CUDA_TRY(cudaGetLastError());
+  return CAAA_OK;
+}
+int caaa_gpu_unpack(const void* d_states_soa, int n, void* d_states_aos, void* cuda_stream) {
+  CAAA_ENTER();
+  if (!g_ctx.ready) return fail(CAAA_E_NOT_INIT, "caaa_gpu_init has not been called");
+  if (!d_states_aos || !d_states_soa || n <= 0 || (reinterpret_cast<uintptr_t>(d_states_soa) & 15u)) return fail(CAAA_E_ARG, "bad unpack arguments");
+  unpack_kernel<<<(n + 31) / 32, 128, 0, (cudaStream_t)cuda_stream>>>((const uint4*)d_states_soa, n, (n + 31) / 32 * 32, (uint8_t*)d_states_aos);
+  CUDA_TRY(cudaGetLastError());
   return CAAA_OK;
 }
 

@@ -209,13 +209,13 @@ CAAA_HD void import_state(Game* g, const uint8_t* src) {
     g->factory_max[l] = ls.factory_max;
     g->bombard_max[l] = ls.bombard_max;
     const uint8_t* u = reinterpret_cast<const uint8_t*>(&ls) + 4;
-#pragma unroll 1
+#pragma unroll 7
     for (int k = 0; k < LU_ROW; k++) g->lu[l][k] = u[k];
   }
 #pragma unroll 1
   for (int s = 0; s < NS; s++) {
     const uint8_t* u = reinterpret_cast<const uint8_t*>(&st->units_sea[s]);
-#pragma unroll 1
+#pragma unroll 19
     for (int k = 0; k < SU_ROW; k++) g->su[s][k] = u[k];
   }
 #pragma unroll 1
@@ -223,16 +223,16 @@ CAAA_HD void import_state(Game* g, const uint8_t* src) {
     const int pa = (cur + p) % NP;
 #pragma unroll 1
     for (int l = 0; l < NL; l++)
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < NLT; u++) utl(g, pa, l)[u] = st->other_land_units[p - 1][l][u];
 #pragma unroll 1
     for (int s = 0; s < NS; s++)
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < NST - 1; u++) uts(g, pa, s)[u] = st->other_sea_units[p - 1][s][u];
   }
   uint32_t sk0 = 0, sk1 = 0;
   const uint8_t* sm = &st->skipped_moves[0][0];
-#pragma unroll 1
+#pragma unroll 8
   for (int i = 0; i < 32; i++) {
     sk0 |= (uint32_t)(sm[i] & 1u) << i;
     sk1 |= (uint32_t)(sm[32 + i] & 1u) << i;
@@ -260,13 +260,13 @@ CAAA_HD void export_state(const Game* g, uint8_t* dst) {
     ls.factory_max = g->factory_max[l];
     ls.bombard_max = g->bombard_max[l];
     uint8_t* u = reinterpret_cast<uint8_t*>(&ls) + 4;
-#pragma unroll 1
+#pragma unroll 7
     for (int k = 0; k < LU_ROW; k++) u[k] = g->lu[l][k];
   }
 #pragma unroll 1
   for (int s = 0; s < NS; s++) {
     uint8_t* u = reinterpret_cast<uint8_t*>(&st->units_sea[s]);
-#pragma unroll 1
+#pragma unroll 19
     for (int k = 0; k < SU_ROW; k++) u[k] = g->su[s][k];
   }
 #pragma unroll 1
@@ -274,15 +274,15 @@ CAAA_HD void export_state(const Game* g, uint8_t* dst) {
     const int pa = (cur + p) % NP;
 #pragma unroll 1
     for (int l = 0; l < NL; l++)
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < NLT; u++) st->other_land_units[p - 1][l][u] = utl(g, pa, l)[u];
 #pragma unroll 1
     for (int s = 0; s < NS; s++)
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < NST - 1; u++) st->other_sea_units[p - 1][s][u] = uts(g, pa, s)[u];
   }
   uint8_t* sm = &st->skipped_moves[0][0];
-#pragma unroll 1
+#pragma unroll 8
   for (int i = 0; i < 64; i++) sm[i] = (uint8_t)((g->skipped[i >> 5] >> (i & 31)) & 1u);
 }
 

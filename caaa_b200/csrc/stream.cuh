@@ -29,7 +29,7 @@ namespace caaa {
 constexpr int NQ = 17;                   // phases 0..14, 15 = end of turn (purchase, bookkeeping, rotation, scoring,
 constexpr int Q_EOT = CAAA_PH_BUY_UNITS; // finish + restart), 16 = free pool entries
 constexpr int Q_FREE = 16;
-constexpr int STREAM_SLOTS = 224;        // shared-memory game slots per CTA
+constexpr int STREAM_SLOTS = 240;        // shared-memory game slots per CTA: 15 warps x 16 games, all of the 227 KB
 constexpr int MAX_POOL_MULT = 4;
 constexpr int MAX_BM_WORDS = STREAM_SLOTS * MAX_POOL_MULT / 32;  // 28 bitmap words per phase
 
@@ -52,6 +52,7 @@ struct StreamShared {
   uint8_t target[STREAM_SLOTS];   // the slot (lane) each claimed entry goes to
 };
 constexpr int STREAM_SMEM = TABLE_BYTES + STREAM_SLOTS * (int)sizeof(Game) + (int)((sizeof(StreamShared) + 15) / 16 * 16);
+static_assert(STREAM_SMEM <= 232448, "phase-regrouped kernel: shared memory budget of one sm_100a CTA");
 
 __global__ void group_init_kernel(GroupState* G, int n_groups, int entries_per_cta, int group_size, int grid) {
   GroupState* gs = G + blockIdx.x;

@@ -13,7 +13,7 @@ SYMBOLS = ["caaa_gpu_init", "caaa_gpu_shutdown", "caaa_gpu_last_error", "caaa_gp
            "caaa_gpu_device_info", "caaa_gpu_rollout_batch", "caaa_gpu_rollout_batch_device",
            "caaa_gpu_synchronize", "caaa_gpu_set_stream", "caaa_gpu_random_play_until_terminal", "caaa_gpu_advance",
            "caaa_gpu_resolve_battles", "caaa_gpu_resolve_battles_device", "caaa_gpu_expand", "caaa_gpu_evaluate",
-           "caaa_gpu_leaf_batch_submit", "caaa_gpu_leaf_batch_collect", "caaa_gpu_set_rollout_sms"]
+           "caaa_gpu_soa_bytes", "caaa_gpu_pack", "caaa_gpu_unpack", "caaa_gpu_leaf_batch_submit", "caaa_gpu_leaf_batch_collect", "caaa_gpu_set_rollout_sms"]
 
 
 # the root-parallel exchange step (NCCL, bound at run time)
@@ -45,6 +45,9 @@ def load_library(path=LIB_PATH):
     lib.caaa_gpu_resolve_battles_device.argtypes = [vp, i32, u64, u64, vp, vp, vp, vp]
     lib.caaa_gpu_expand.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.caaa_gpu_evaluate.argtypes = [vp, i32, vp]
+    lib.caaa_gpu_soa_bytes.argtypes = [i32, vp]
+    lib.caaa_gpu_pack.argtypes = [vp, i32, vp, vp]
+    lib.caaa_gpu_unpack.argtypes = [vp, i32, vp, vp]
     lib.caaa_gpu_leaf_batch_submit.argtypes = [i32, vp, i32, i32, u64, u64, vp]
     lib.caaa_gpu_leaf_batch_collect.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.caaa_gpu_set_rollout_sms.argtypes = [i32]
@@ -170,6 +173,17 @@ class GpuEngine:
                                                          out["sums"].ctypes.data, out["summary"].ctypes.data))
         out["summary"] = out["summary"][0]
         return out
+
+    def soa_bytes(self, n):
+        b = C.c_size_t(0)
+        self._check(self.lib.caaa_gpu_soa_bytes(int(n), C.byref(b)))
+        return b.value
+
+    def pack(self, d_aos_ptr, n, d_soa_ptr, stream_ptr=None):
+        self._check(self.lib.caaa_gpu_pack(d_aos_ptr, int(n), d_soa_ptr, stream_ptr))
+
+    def unpack(self, d_soa_ptr, n, d_aos_ptr, stream_ptr=None):
+        self._check(self.lib.caaa_gpu_unpack(d_soa_ptr, int(n), d_aos_ptr, stream_ptr))
 
     def set_rollout_sms(self, sms):
         self._check(self.lib.caaa_gpu_set_rollout_sms(int(sms)))

@@ -16,6 +16,8 @@
 #ifndef CAAA_GPU_H
 #define CAAA_GPU_H
 
+#include <stddef.h>
+
 #include "caaa_types.h"
 
 #ifdef __cplusplus
@@ -104,6 +106,15 @@ int caaa_gpu_resolve_battles_device(const void* d_states, int n, uint64_t seed, 
  * action k, bit 31 = computing the action list itself. */
 int caaa_gpu_expand(const CaaaGameState* leaves, int n, uint8_t* n_actions, uint8_t* actions,
                     CaaaGameState* children, uint32_t* status);
+
+/* AoS <-> SoA (SURVEY.md 8b `caaa_gpu_pack/unpack`): the chunk-major structure-of-arrays form of a batch of states --
+ * 42 chunks of 16 bytes per state; chunk c of state i at byte (c * n_pad + i) * 16, n_pad = n rounded up to 32 -- in
+ * which 32 consecutive states are read with one 512-byte LDG.128 per chunk.  Device pointers (SoA 16-byte aligned,
+ * caaa_gpu_soa_bytes(n) bytes), asynchronous on `cuda_stream`.  DESIGN.md section 3 records where this layout was
+ * measured against the array-of-records form the kernels use. */
+int caaa_gpu_soa_bytes(int n, size_t* bytes);
+int caaa_gpu_pack(const void* d_states_aos, int n, void* d_states_soa, void* cuda_stream);
+int caaa_gpu_unpack(const void* d_states_soa, int n, void* d_states_aos, void* cuda_stream);
 
 /* ---- Asynchronous leaf batches: one MCTS iteration's device work for n leaves at once (reference src/mcts.cpp:78-94:
  * is_terminal_state, expand_node, `rand() % num_children`, random_play_until_terminal), without a host round trip

@@ -9,7 +9,7 @@
 //          the first playout of state 0 (= 0 unless CAAA_REF_ID0 is set); per_state = 0 / absent: always state 0.
 //          stats_out.bin receives one 32-byte CaaaRolloutStats per playout.
 //        prints one line: playouts plies decisions draws seconds sum_result
-//        ref_cli mcts <state.bin> <iterations>
+//        ref_cli mcts <state.bin> <iterations> [literal]    (literal: without the per-playout valid_moves reset, P1 iv)
 //          prints: iterations seconds  then one line per root child: action visits value   and "best <action>"
 #include "../include/caaa_types.h"
 #include <chrono>
@@ -24,6 +24,7 @@ void caaa_ref_rollout_many(const void* state670, int64_t first_game_id, int n, C
                            double* results);
 int caaa_ref_mcts(const void* state670, long iterations, uint8_t* actions, int32_t* visits, double* values,
                   uint8_t* best_action);
+void caaa_ref_set_reset_valid_moves(int on);
 }
 
 static unsigned char* read_states(const char* path, long* n_states) {
@@ -58,6 +59,7 @@ int main(int argc, char** argv) {
     long iters = atol(argv[3]);
     caaa_ref_init();
     caaa_ref_set_stream(0, 0);  // the reference's own glibc stream
+    if (argc > 4 && strcmp(argv[4], "literal") == 0) caaa_ref_set_reset_valid_moves(0);  // P0 behaviour: SURVEY Appendix E
     uint8_t actions[CAAA_ACTIONS], best = 255;
     int32_t visits[CAAA_ACTIONS];
     double values[CAAA_ACTIONS];

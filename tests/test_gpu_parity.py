@@ -161,13 +161,13 @@ def test_regrouped_kernel_small_batches_vs_oracle(port, tmp_path):
 
 
 def test_ragged_batches_vs_oracle(eng, port):
-    """Batch shapes around the kernel's internal sizes (32 lanes, 224 slots per SM, 16 games per warp): one game,
+    """Batch shapes around the kernel's internal sizes (32 lanes, 240 slots per SM, 16 games per warp): one game,
     partial warps, partial CTAs, several start states with one or a few playouts each."""
     s0 = layout.start_state()
     seed = 0xBA7C4
     port.set_stream(1, seed)
     first = 123456
-    for n in (1, 2, 15, 17, 31, 33, 223, 225, 449):
+    for n in (1, 2, 15, 17, 31, 33, 223, 225, 239, 241, 449, 481):
         _, got, summ = eng.rollout_batch(s0, n, seed, first, want_stats=True)
         assert np.array_equal(got, port.rollout_many(s0, first, n)), n
         assert summ["playouts"] == n
@@ -181,9 +181,9 @@ def test_ragged_batches_vs_oracle(eng, port):
 
 
 def test_lockstep_and_regrouped_kernels_agree(tmp_path):
-    """The walk-the-pipeline kernel (CAAA_ROLLOUT_KERNEL=lockstep, with and without the per-phase CTA barrier) and the
-    phase-regrouped kernel with other warp widths play the same playouts bit for bit (separate processes: the
-    library reads its knobs once at init)."""
+    """The walk-the-pipeline kernel (CAAA_ROLLOUT_KERNEL=lockstep, with and without the per-phase CTA barrier), the
+    phase-regrouped kernel with other group sizes and with yielding phases, and the SM-resident experiment
+    (CAAA_ROLLOUT_KERNEL=resident) play the same playouts bit for bit."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -193,8 +193,9 @@ def test_lockstep_and_regrouped_kernels_agree(tmp_path):
     outs = []
     for k, env in enumerate(({"CAAA_ROLLOUT_KERNEL": "stream"}, {"CAAA_ROLLOUT_KERNEL": "lockstep"},
                              {"CAAA_ROLLOUT_KERNEL": "lockstep", "CAAA_SYNC": "1"},
-                             {"CAAA_ROLLOUT_KERNEL": "stream", "CAAA_LANES": "32", "CAAA_GROUP": "1"},
-                             {"CAAA_ROLLOUT_KERNEL": "stream", "CAAA_LANES": "8", "CAAA_YIELD": "75"})):
+                             {"CAAA_ROLLOUT_KERNEL": "stream", "CAAA_GROUP": "1"},
+                             {"CAAA_ROLLOUT_KERNEL": "stream", "CAAA_YIELD": "50", "CAAA_YIELD_BATTLES": "25"},
+                             {"CAAA_ROLLOUT_KERNEL": "resident", "CAAA_WARPS": "12", "CAAA_YIELD": "50"})):
         out = str(tmp_path / f"k{k}.npy")
         subprocess.check_call([sys.executable, "-c", code, out], env={**os.environ, **env})
         outs.append(np.load(out))
@@ -294,3 +295,26 @@ def test_mcts_search_on_gpu(eng):
     # pure purchases of the first mover cannot change the material ratio much: all children's means are close
     means = x3 / np.maximum(v3, 1)
     assert means.max() - means.min() < 0.2
+
+
+def test_soa_pack_unpack_round_trip(eng):
+    """caaa_gpu_pack / caaa_gpu_unpack: chunk-major SoA form and back, ragged sizes; chunk c of state i sits where the
+    header says, pad bytes are zero."""
+    import torch
+    a = np.load(os.path.join(GOLD, "advance.npz"))["states"]
+    for n in (1, 31, 32, 33, 96):
+        st = np.ascontiguousarray(a[:n])
+        d_aos = torch.from_numpy(st).cuda()
+        nb = eng.soa_bytes(n)
+        n_pad = (n + 31) // 32 * 32
+        assert nb == 42 * n_pad * 16
+        d_soa = torch.full((nb,), 0xAB, dtype=torch.uint8, device="cuda")
+        d_back = torch.zeros_like(d_aos)
+        eng.pack(d_aos.data_ptr(), n, d_soa.data_ptr())
+        eng.unpack(d_soa.data_ptr(), n, d_back.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_back.cpu().numpy(), st)
+        soa = d_soa.cpu().numpy().reshape(42, n_pad, 16)
+        padded = np.zeros((n, 672), dtype=np.uint8)
+        padded[:, :670] = st
+        assert np.array_equal(soa[:, :n, :].transpose(1, 0, 2).reshape(n, 672), padded)

@@ -4,6 +4,8 @@ The reference ships no tests or golden vectors, so the por
 against the reference's own functions on the same inputs: whole playouts, every phase of the
 pipeline with all derived caches, and the stop-at-decision mode used for tree expansion.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -125,3 +127,20 @@ def test_expansion_mode_bit_exact(ref, port):
         b = port.rollout_many(sp, walk * 10, 4)
         assert np.array_equal(a, b), walk
     print("actions skipped because the reference would hang:", n_stuck)
+
+
+def test_reference_mcts_known_answer_appendix_e(tmp_path):
+    """BASELINE config 1 pinned: the reference's own mcts_search (src/mcts.cpp:65-108), 20 000 iterations from the start
+    position on its own byte stream, reproduces SURVEY.md Appendix E's root statistics exactly."""
+    import subprocess
+    from caaa_b200 import layout
+    cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "ref_cli")
+    if not os.path.exists(cli):
+        pytest.skip("oracle/_ref/ref_cli not built")
+    p = str(tmp_path / "s0.bin")
+    layout.start_state().tofile(p)
+    out = subprocess.run([cli, "mcts", p, "20000", "literal"], capture_output=True, text=True).stdout
+    kids = [l.split() for l in out.splitlines() if l.startswith("CHILD")]
+    assert [(int(k[1]), int(k[2])) for k in kids] == [(6, 892), (5, 4664), (4, 5166), (3, 3693), (2, 5054), (0, 531)]
+    assert [round(float(k[3]), 2) for k in kids] == [775.97, 4444.87, 4940.16, 3489.80, 4829.48, 438.85]
+    assert "BEST 4" in out

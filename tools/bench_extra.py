@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Secondary measurements (BASELINE.json configs 3, 4, 5); bench.py is the headline (config 2).
 
+    python tools/bench_extra.py config1 [--iterations 100000]          (CPU only: the reference's own search)
     python tools/bench_extra.py battles [--n 10485760]
     python tools/bench_extra.py leaf    [--leaves 1024 --rollouts 4096]
     [torchrun --nproc-per-node N] python tools/bench_extra.py mcts [--iterations 2048 --rollouts 4096 --leaves-per-batch 64]
@@ -121,16 +122,43 @@ def mcts(args):
         dist.destroy_process_group()
 
 
+def config1(args):
+    """BASELINE config 1: the reference's own mcts_search (reference src/mcts.cpp:65-108) from the start position, fixed
+    iteration count, ONE CPU thread, the reference's own glibc byte stream and literal behaviour (no per-playout
+    valid_moves reset), i.e. the build SURVEY.md Appendix E took its known answers from."""
+    import subprocess
+    import tempfile
+    cli = os.path.join(ROOT, "oracle", "_ref", "ref_cli")
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        path = f.name
+    layout.start_state().tofile(path)
+    out = subprocess.run([cli, "mcts", path, str(args.iterations), "literal"], capture_output=True, text=True).stdout
+    os.unlink(path)
+    secs, children, best = None, [], None
+    for line in out.splitlines():
+        f = line.split()
+        if f[:1] == ["MCTS"]:
+            secs = float(f[2])
+        elif f[:1] == ["CHILD"]:
+            children.append({"action": int(f[1]), "visits": int(f[2]), "value": float(f[3])})
+        elif f[:1] == ["BEST"]:
+            best = int(f[1])
+    print(json.dumps({"workload": "config 1: reference mcts_search from the start position, one CPU thread (oracle/_ref/ref_cli mcts)",
+                      "iterations": args.iterations, "seconds": secs, "iterations_per_sec": args.iterations / secs,
+                      "root_children": children, "best_action": best, "cores": 1,
+                      "appendix_e": "20 000 iterations -> visits 892/4664/5166/3693/5054/531, best 4; 100 000 -> best 2"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["battles", "leaf", "mcts"])
+    ap.add_argument("what", choices=["battles", "leaf", "mcts", "config1"])
     ap.add_argument("--n", type=int, default=10 * (1 << 20))
     ap.add_argument("--leaves", type=int, default=1024)
     ap.add_argument("--rollouts", type=int, default=4096)
     ap.add_argument("--iterations", type=int, default=1024)
     ap.add_argument("--leaves-per-batch", type=int, default=64)
     args = ap.parse_args()
-    {"battles": battles, "leaf": leaf, "mcts": mcts}[args.what](args)
+    {"battles": battles, "leaf": leaf, "mcts": mcts, "config1": config1}[args.what](args)
 
 
 if __name__ == "__main__":
