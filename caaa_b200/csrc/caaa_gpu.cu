@@ -69,6 +69,7 @@ struct RolloutArgs {
   int min_batch_polls;
   unsigned idle_ns;     // sleep of an idle warp between two looks at the queues
   int* abort_flag;      // set when the watchdog gave up (global memory, optional)
+  int patience;         // pool kernel: empty claims in a row before a CTA leaves its phase (0 = round 1's queue-length rule)
 };
 
 // Import every start / leaf state once: reference layout -> Game with all derived caches, ready to be
@@ -497,7 +498,7 @@ struct Context {
   long long small_batch = 32768;  // batches up to this size go to the lockstep kernel (no pool hops: lower latency);
                                   // CAAA_ROLLOUT_KERNEL=stream sets it to 0
   int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
-  int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 8 | 16 | 32)
+  int lanes = 20;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 16 | 20 | 24): 12 warps x 20 games per SM
   int group_size = 16;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
   LaunchSlot slots[N_LAUNCH_SLOTS];  // per-launch scratch: launches on different streams may be in flight together
   int next_slot = 0;
@@ -621,6 +622,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.min_batch_polls = env_int("CAAA_MIN_BATCH_POLLS", 8);
   a.idle_ns = (unsigned)env_int("CAAA_IDLE_NS", 100);
   a.abort_flag = L.d_abort;
+  a.patience = env_int("CAAA_PATIENCE", 4);
   {  // which kernel: CAAA_ROLLOUT_KERNEL = resident | stream | lockstep forces one; default = by batch size
     const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
     const long long small = env_int("CAAA_SMALL_BATCH", (int)c.small_batch);
@@ -694,11 +696,18 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
 #define CAAA_LAUNCH_STREAM(NL)                                                                                                       \
   do {                                                                                                                              \
     if (d_stats)                                                                                                                    \
-      rollout_kernel_stream<true, NL><<<grid, STREAM_SLOTS / NL * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg);  \
+      rollout_kernel_stream<true, NL><<<grid, stream_threads, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg);  \
     else                                                                                                                            \
-      rollout_kernel_stream<false, NL><<<grid, STREAM_SLOTS / NL * 32, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
+      rollout_kernel_stream<false, NL><<<grid, stream_threads, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
   } while (0)
-    CAAA_LAUNCH_STREAM(16);  // (8 and 32 games per warp were measured: 0.91 M and 1.23 M playouts/s against 1.30 M)
+    const int lanes = env_int("CAAA_LANES", c.lanes) == 24 ? 24 : env_int("CAAA_LANES", c.lanes) == 20 ? 20 : 16;
+    int stream_warps = env_int("CAAA_STREAM_WARPS", STREAM_SLOTS / lanes);  // A/B knob: fewer warps leave slots unused
+    if (stream_warps < 1 || stream_warps > STREAM_SLOTS / lanes) stream_warps = STREAM_SLOTS / lanes;
+    const int stream_threads = stream_warps * 32;
+    if (lanes == 24) CAAA_LAUNCH_STREAM(24);
+    else if (lanes == 20) CAAA_LAUNCH_STREAM(20);
+    else CAAA_LAUNCH_STREAM(16);  // (measured with the sticky phase rule: 16 / 20 / 24 games per warp = 1.35 / 1.40 / 1.39 M playouts/s;
+                                  //  8 and 32 under round 1's rule: 0.91 M and 1.23 M against 1.30 M)
     if (d_dbg != nullptr) {
       StreamDbg h;
       cudaStreamSynchronize(stream);
@@ -707,6 +716,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
       std::fprintf(stderr, "stream dbg: batches %llu items/batch %.1f  idle+claim %.3f in %.3f compute %.3f restart %.3f out %.3f  Mcyc/warp %.1f\n",
                    h.batches, h.batches ? (double)h.items / (double)h.batches : 0.0, h.t[0] / tt, h.t[1] / tt, h.t[2] / tt, h.t[3] / tt,
                    h.t[4] / tt, tt / (grid * (STREAM_SLOTS / c.lanes)) / 1e6);
+      std::fprintf(stderr, "stream dbg: CTA kind switches %llu = one per %.1f batches of the CTA\n", h.t[5], h.t[5] ? (double)h.batches / (double)h.t[5] : 0.0);
       std::fprintf(stderr, "stream dbg: per kind  share of phase time / share of game visits:");
       double kc = 0, ki = 0;
       for (int q = 0; q < NQ; q++) { kc += (double)h.kind_cycles[q]; ki += (double)h.kind_items[q]; }
@@ -774,12 +784,16 @@ int caaa_gpu_init(int device) {
   if (c.pool_mult < 1) c.pool_mult = 1;
   if (c.pool_mult > MAX_POOL_MULT) c.pool_mult = MAX_POOL_MULT;
   const char* ln = std::getenv("CAAA_LANES");
-  (void)ln;
-  c.lanes = 16;
+  c.lanes = ln ? std::atoi(ln) : 20;
+  if (c.lanes != 16 && c.lanes != 24) c.lanes = 20;
   const char* gs = std::getenv("CAAA_GROUP");
   c.group_size = gs ? std::atoi(gs) : 16;
   if (c.group_size < 1) c.group_size = 1;
   if (c.group_size > MAX_GROUP) c.group_size = MAX_GROUP;
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_resident<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM));

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   constexpr int KW = (GAME_WORDS + 31) / 32;
   LaneTotals tot;
   long long last_work = clock64();
+  int seen_kind = -2, empty_polls = 0;
   unsigned long long d_batches = 0, d_items = 0, d_t[6] = {0, 0, 0, 0, 0, 0};
   long long d_c0 = clock64();
 #define CAAA_LAP(k)                                   \
@@ -281,9 +282,30 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   for (;;) {
     // ---- choose a phase: the CTA's current one while enough entries wait for it, else the one with the most
     // entries per serving CTA (ties go to the later phase, which is closer to finishing a turn) ----
-    const int c = lane < NQ ? vcnt[lane] : 0;
+    // Stickiness matters more than queue length: the SMs of a GPC share one instruction cache behind their own, and
+    // round 1's rule (leave a phase as soon as fewer than 8 entries wait for it) made a CTA change phase every 3.2
+    // batches -- its 15 warps were in ~5 different phase functions at any time, the SM instruction cache hit rate was
+    // 78 % and the GPC-level cache ran at 91 % of its request rate: THE limiter of the kernel (profiles/r2_summary.md).
+    // With `patience` > 0 a CTA keeps its phase until a warp has found its queue empty `patience` times in a row
+    // (sleeping in between, while other CTAs publish into it), and only then moves on.
     int kind = *vkind;
-    if (kind < 0 || __shfl_sync(FULL, c, kind) < switch_below) {
+    if (kind != seen_kind) {
+      seen_kind = kind;
+      empty_polls = 0;
+    }
+    int c = 0;
+    bool pick = kind < 0;
+    if (!pick) {
+      if (a.patience > 0) {
+        pick = empty_polls >= a.patience;
+      } else {
+        c = lane < NQ ? vcnt[lane] : 0;
+        pick = __shfl_sync(FULL, c, kind) < switch_below;
+      }
+    }
+    if (pick) {
+      if (a.patience > 0 || kind < 0) c = lane < NQ ? vcnt[lane] : 0;
+      empty_polls = 0;
       const int srv = lane < NQ ? vsrv[lane] - (lane == kind ? 1 : 0) : 0;
       const unsigned score = c > 0 ? (unsigned)((c << 4) / (srv + 1)) + 1u : 0u;
       const unsigned key = __reduce_max_sync(FULL, score ? (score << 5) | (unsigned)lane : 0u);
@@ -308,16 +330,23 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         if (old != nk) {
           if (old >= 0) atomicSub(&GS->servers[old], 1);
           atomicAdd(&GS->servers[nk], 1);
+          if (dbg != nullptr) atomicAdd(&dbg->t[5], 1ULL);  // kind switches of CTAs
         }
       }
       kind = nk;
+      seen_kind = nk;
     }
     bool have = false;   // this lane holds a game of phase `kind`
     unsigned idx = 0;    // its pool entry
     {  // ---- serve `kind`: claim a batch, run it, route the games on ----
       const unsigned free_lanes = LANE_MASK;
       const int n_new = claim(kind, LANES);
-      if (n_new == 0) continue;
+      if (n_new == 0) {
+        empty_polls++;
+        if (a.patience > 0) __nanosleep(a.idle_ns);
+        continue;
+      }
+      empty_polls = 0;
       CAAA_LAP(0);  // idle + select + claim
       if (n_new > 0) {
         last_work = clock64();
