@@ -602,8 +602,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.summary = d_summary;
   a.ticket = L.d_ticket;
   {
-    const char* sb = std::getenv("CAAA_SWITCH_BELOW");
-    a.switch_below = sb ? std::atoi(sb) : 8;
+    a.switch_below = 0;  // (round 1's queue-length rule; replaced by `patience`)
     const char* yl = std::getenv("CAAA_YIELD");
     a.yield_lanes = yl ? std::atoi(yl) : 0;
     const char* yb = std::getenv("CAAA_YIELD_BATTLES");
@@ -623,6 +622,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.idle_ns = (unsigned)env_int("CAAA_IDLE_NS", 100);
   a.abort_flag = L.d_abort;
   a.patience = env_int("CAAA_PATIENCE", 4);
+  if (a.patience < 1) a.patience = 1;
   {  // which kernel: CAAA_ROLLOUT_KERNEL = resident | stream | lockstep forces one; default = by batch size
     const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
     const long long small = env_int("CAAA_SMALL_BATCH", (int)c.small_batch);
@@ -695,7 +695,9 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
     }
 #define CAAA_LAUNCH_STREAM(NL)                                                                                                       \
   do {                                                                                                                              \
-    if (d_stats)                                                                                                                    \
+    if (d_dbg)                                                                                                                      \
+      rollout_kernel_stream<false, NL, true><<<grid, stream_threads, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
+    else if (d_stats)                                                                                                               \
       rollout_kernel_stream<true, NL><<<grid, stream_threads, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg);  \
     else                                                                                                                            \
       rollout_kernel_stream<false, NL><<<grid, stream_threads, STREAM_SMEM, stream>>>(a, (uint32_t*)L.d_pool, c.pool_mult, d_groups, c.group_size, d_dbg); \
@@ -790,6 +792,9 @@ int caaa_gpu_init(int device) {
   c.group_size = gs ? std::atoi(gs) : 16;
   if (c.group_size < 1) c.group_size = 1;
   if (c.group_size > MAX_GROUP) c.group_size = MAX_GROUP;
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));

@@ -194,7 +194,9 @@ __device__ __forceinline__ int run_kind(int kind, Game* g, const RunCtx cx, unsi
 // for it, runs the phase on them in lockstep and routes them on.  Optionally (yield_lanes / yield_battles, off by
 // default: measured neutral) a phase yields once a share of its batch is done; the stragglers keep their loop cursor
 // in the game (engine2.cuh), are queued for the same phase again and meet other stragglers there.
-template <bool STATS, int LANES>
+// DBG = per-section cycle accounting (CAAA_DEBUG); compiled out of the shipped instantiation: the scheduler loop is
+// hot in the instruction caches of every SM, and a few dozen instructions there cost 2 % of the throughput.
+template <bool STATS, int LANES, bool DBG = false>
 __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_stream(const RolloutArgs a, uint32_t* pool_all, int pool_mult,
                                                                                        GroupState* groups, int group_size, StreamDbg* dbg) {
   const DevTables* T = stage_tables(a.tables);
@@ -218,7 +220,6 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   volatile int* vkind = &S->kind;
   volatile int* vretired = &GS->retired;
   unsigned scan_rot = (unsigned)((blockIdx.x * 7 + warp * 3) * 32) % (unsigned)(((bm_words + 31) / 32) * 32);  // where this warp starts scanning
-  const int switch_below = a.switch_below;  // leave a phase when fewer entries than this wait for it
   constexpr unsigned LANE_MASK = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
   constexpr int KW = (GAME_WORDS + 31) / 32;
   LaneTotals tot;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   long long d_c0 = clock64();
 #define CAAA_LAP(k)                                   \
   do {                                                \
-    if (dbg != nullptr) {                             \
+    if (DBG) {                                        \
       const long long c_ = clock64();                 \
       d_t[k] += (unsigned long long)(c_ - d_c0);      \
       d_c0 = c_;                                      \
@@ -293,18 +294,8 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       seen_kind = kind;
       empty_polls = 0;
     }
-    int c = 0;
-    bool pick = kind < 0;
-    if (!pick) {
-      if (a.patience > 0) {
-        pick = empty_polls >= a.patience;
-      } else {
-        c = lane < NQ ? vcnt[lane] : 0;
-        pick = __shfl_sync(FULL, c, kind) < switch_below;
-      }
-    }
-    if (pick) {
-      if (a.patience > 0 || kind < 0) c = lane < NQ ? vcnt[lane] : 0;
+    if (kind < 0 || empty_polls >= a.patience) {
+      const int c = lane < NQ ? vcnt[lane] : 0;
       empty_polls = 0;
       const int srv = lane < NQ ? vsrv[lane] - (lane == kind ? 1 : 0) : 0;
       const unsigned score = c > 0 ? (unsigned)((c << 4) / (srv + 1)) + 1u : 0u;
@@ -330,7 +321,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         if (old != nk) {
           if (old >= 0) atomicSub(&GS->servers[old], 1);
           atomicAdd(&GS->servers[nk], 1);
-          if (dbg != nullptr) atomicAdd(&dbg->t[5], 1ULL);  // kind switches of CTAs
+          if (DBG) atomicAdd(&dbg->t[5], 1ULL);  // kind switches of CTAs
         }
       }
       kind = nk;
@@ -343,15 +334,17 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       const int n_new = claim(kind, LANES);
       if (n_new == 0) {
         empty_polls++;
-        if (a.patience > 0) __nanosleep(a.idle_ns);
+        __nanosleep(a.idle_ns);
         continue;
       }
       empty_polls = 0;
       CAAA_LAP(0);  // idle + select + claim
       if (n_new > 0) {
         last_work = clock64();
-        d_batches++;
-        d_items += (unsigned)n_new;
+        if (DBG) {
+          d_batches++;
+          d_items += (unsigned)n_new;
+        }
         fence_gpu();
         // the j-th new entry goes to the j-th free lane
         const int my_rank = __popc(free_lanes & ((1u << lane) - 1u));
@@ -399,7 +392,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       bool live = runs, need_start = false;
       if (runs) res = run_kind<STATS>(kind, g, cx, mhave, yield, a, tot, live, need_start);
       __syncwarp();
-      if (dbg != nullptr && lane == 0) {
+      if (DBG && lane == 0) {
         atomicAdd(&dbg->kind_cycles[kind], (unsigned long long)(clock64() - d_c0));
         atomicAdd(&dbg->kind_items[kind], (unsigned long long)n_new);
       }
@@ -449,7 +442,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
     }
   }
 #undef CAAA_LAP
-  if (dbg != nullptr && lane == 0) {
+  if (DBG && lane == 0) {
     atomicAdd(&dbg->batches, d_batches);
     atomicAdd(&dbg->items, d_items);
     for (int k = 0; k < 6; k++) atomicAdd(&dbg->t[k], d_t[k]);
