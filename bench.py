@@ -42,7 +42,7 @@ METRIC = "playouts/sec"
 # kernels of one rollout batch: prepare_kernel (import of the start states), group_init_kernel (phase bitmaps),
 # rollout_kernel_stream (the playouts)
 KERNELS_PER_BATCH = 3
-ROLLOUT_KERNEL = "rollout_kernel_stream<false, 20>"
+ROLLOUT_KERNEL = "rollout_kernel_stream<false, 16>"
 # counters of one rollout_kernel_stream launch of 2**20 playouts, exported from the ncu capture of this command
 NCU_COUNTERS = os.path.join(ROOT, "profiles", "r2_rollout_counters.json")
 

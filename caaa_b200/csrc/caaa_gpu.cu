@@ -498,8 +498,8 @@ struct Context {
   long long small_batch = 32768;  // batches up to this size go to the lockstep kernel (no pool hops: lower latency);
                                   // CAAA_ROLLOUT_KERNEL=stream sets it to 0
   int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
-  int lanes = 20;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 16 | 20 | 24): 12 warps x 20 games per SM
-  int group_size = 16;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP)
+  int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 16 | 20 | 24): 15 warps x 16 games per SM
+  int group_size = 74;       // CTAs that share one game pool and one set of phase bitmaps (CAAA_GROUP): two groups per B200
   LaunchSlot slots[N_LAUNCH_SLOTS];  // per-launch scratch: launches on different streams may be in flight together
   int next_slot = 0;
   std::atomic_flag busy = ATOMIC_FLAG_INIT;  // the context is single-caller: concurrent entry is refused (CAAA_E_BUSY)
@@ -621,7 +621,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.min_batch_polls = env_int("CAAA_MIN_BATCH_POLLS", 8);
   a.idle_ns = (unsigned)env_int("CAAA_IDLE_NS", 100);
   a.abort_flag = L.d_abort;
-  a.patience = env_int("CAAA_PATIENCE", 4);
+  a.patience = env_int("CAAA_PATIENCE", 6);
   if (a.patience < 1) a.patience = 1;
   {  // which kernel: CAAA_ROLLOUT_KERNEL = resident | stream | lockstep forces one; default = by batch size
     const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");
@@ -786,12 +786,13 @@ int caaa_gpu_init(int device) {
   if (c.pool_mult < 1) c.pool_mult = 1;
   if (c.pool_mult > MAX_POOL_MULT) c.pool_mult = MAX_POOL_MULT;
   const char* ln = std::getenv("CAAA_LANES");
-  c.lanes = ln ? std::atoi(ln) : 20;
-  if (c.lanes != 16 && c.lanes != 24) c.lanes = 20;
+  c.lanes = ln ? std::atoi(ln) : 16;
+  if (c.lanes != 20 && c.lanes != 24) c.lanes = 16;
   const char* gs = std::getenv("CAAA_GROUP");
-  c.group_size = gs ? std::atoi(gs) : 16;
+  c.group_size = gs ? std::atoi(gs) : 74;
   if (c.group_size < 1) c.group_size = 1;
   if (c.group_size > MAX_GROUP) c.group_size = MAX_GROUP;
+  while ((long long)c.group_size * STREAM_SLOTS * c.pool_mult > 65536) c.group_size--;  // pool entries are 16-bit indices
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 20, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel_stream<false, 24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STREAM_SMEM));

@@ -33,7 +33,8 @@ constexpr int STREAM_SLOTS = 240;        // shared-memory game slots per CTA: 15
 constexpr int MAX_POOL_MULT = 4;
 constexpr int MAX_BM_WORDS = STREAM_SLOTS * MAX_POOL_MULT / 32;  // 28 bitmap words per phase
 
-constexpr int MAX_GROUP = 16;            // SMs that share one pool and one set of phase bitmaps
+constexpr int MAX_GROUP = 74;            // most SMs that may share one pool and one set of phase bitmaps: pool entries are
+                                         // 16-bit indices, 74 x 480 = 35 520 of them
 constexpr int MAX_BM_WORDS_G = MAX_BM_WORDS * MAX_GROUP;
 
 // One per group of CTAs, in global memory (L2): the CTAs of a group pool their games, so that a CTA finds
@@ -53,6 +54,7 @@ struct StreamShared {
 };
 constexpr int STREAM_SMEM = TABLE_BYTES + STREAM_SLOTS * (int)sizeof(Game) + (int)((sizeof(StreamShared) + 15) / 16 * 16);
 static_assert(STREAM_SMEM <= 232448, "phase-regrouped kernel: shared memory budget of one sm_100a CTA");
+static_assert(MAX_GROUP * STREAM_SLOTS * MAX_POOL_MULT <= 65536 * 2 && MAX_GROUP * STREAM_SLOTS * 2 <= 65536, "pool entries are 16-bit indices at the default pool size");
 
 __global__ void group_init_kernel(GroupState* G, int n_groups, int entries_per_cta, int group_size, int grid) {
   GroupState* gs = G + blockIdx.x;
