@@ -1,12 +1,12 @@
 // caaa_gpu.cu -- sm_100a kernels and the C-ABI of libcaaa_gpu.so (include/caaa_gpu.h).
 //
-// Execution model: one persistent CTA per SM; 224 games (7 warps x 32 lanes, one game per
-// lane) and the topology tables stay resident in the CTA's 227 KB of shared memory for the whole
-// playout, so the only HBM traffic of a playout is its start state in and its result out.  All 32 lanes
-// of a warp walk the turn pipeline together (engine2.cuh is written so that they stay converged:
-// flat cursor loops, per-game work masks).  Finished games are replaced from a global ticket counter by
-// a warp-cooperative copy of the pre-imported start state, which absorbs the long tail of game
-// lengths.  No tensor cores: the work is branchy uint8 arithmetic.
+// Execution model.  One thread plays one game; a game's working set (`Game`, 932 bytes) lives in
+// shared memory while a warp works on it.  Large batches run in rollout_kernel_stream (stream.cuh): persistent, one CTA
+// per SM, games regrouped by phase through an L2-resident pool so that a warp's lanes all have work in the phase it
+// runs and a CTA's warps share one phase's instructions.  Small batches (<= 12 288 playouts) run in rollout_kernel
+// below, which keeps every game in its lane for life and walks the turn pipeline (no pool traffic, lowest latency).
+// Finished games are replaced from a global ticket counter by a warp-cooperative copy of the pre-imported start
+// state, which absorbs the long tail of game lengths.  No tensor cores: the work is branchy uint8 arithmetic.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -30,7 +30,7 @@ using namespace e2;
 
 constexpr int TABLE_BYTES = (int)((sizeof(DevTables) + 15) / 16 * 16);
 constexpr int GAME_WORDS = (int)(sizeof(Game) / 4);
-constexpr int ROLLOUT_WARPS = 7;                     // 7 x 32 games x 924 B + tables = 208,336 B of shared memory
+constexpr int ROLLOUT_WARPS = 7;                     // lockstep kernel: 7 x 32 games x 932 B + tables = 210 KB of shared memory
 constexpr int ROLLOUT_THREADS = ROLLOUT_WARPS * 32;  // one game per thread
 constexpr int SMALL_THREADS = 128;                   // non-persistent kernels
 constexpr unsigned FULL = 0xffffffffu;
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(ROLLOUT_THREADS, 1) rollout_kernel(const Rollo
   LaneTotals tot;
   for (;;) {
     // ---- refill idle lanes at a turn boundary: one ticket fetch per warp, then all 32 lanes copy each
-    // new game's 231 words from the pre-imported state (coalesced, converged) ----
+    // new game's 233 words from the pre-imported state (coalesced, converged) ----
     const unsigned need = __ballot_sync(FULL, !live && !exhausted);
     if (need) {
       unsigned long long base = 0;
@@ -495,7 +495,8 @@ struct Context {
   int kernel = 1;            // kernel of the most recent launch: 0 = SM-resident, 1 = phase-regrouped over a global pool, 2 = lockstep
   int small_kernel = 2;      // the kernel for batches of up to small_batch playouts
   int res_warps = 16;        // warps per CTA of the resident kernel (CAAA_WARPS)
-  long long small_batch = 32768;  // batches up to this size go to the lockstep kernel (no pool hops: lower latency);
+  long long small_batch = 12288;  // batches up to this size go to the lockstep kernel (no pool hops: lower latency;
+                                  // measured: 4 096 playouts 76 vs 82 ms, 24 576 playouts 100 vs 82 ms);
                                   // CAAA_ROLLOUT_KERNEL=stream sets it to 0
   int pool_mult = 2;         // pool entries per shared-memory slot (CAAA_POOL_MULT); 2 keeps the 62 MB pool L2-resident
   int lanes = 16;            // games per warp of the phase-regrouped kernel (CAAA_LANES = 16 | 20 | 24): 15 warps x 16 games per SM
@@ -567,7 +568,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   const unsigned long long n_games = (unsigned long long)n_states * rollouts_per_state;
   const size_t tmpl_bytes = ((size_t)n_states * sizeof(Game) + 7) / 8 * 8;
   const size_t tmpl_need = tmpl_bytes + (size_t)n_states * sizeof(double);
-  const size_t pool_need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game) + 16 +
+  const size_t pool_need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(PoolGame) + 16 +
                            (size_t)((c.sm_count + c.group_size - 1) / c.group_size) * sizeof(GroupState) + sizeof(StreamDbg) + sizeof(ResDbg);
   if (L.used) {
     if (tmpl_need > L.templates_cap || pool_need > L.pool_cap) CUDA_TRY(cudaEventSynchronize(L.done));  // buffers are about to be replaced
@@ -683,7 +684,7 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   const unsigned long long sms = (unsigned long long)(c.rollout_sms > 0 && c.rollout_sms < c.sm_count ? c.rollout_sms : c.sm_count);
   const int grid = (int)(want < sms ? want : sms);
   if (c.kernel == 1) {
-    const size_t need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(Game);
+    const size_t need = (size_t)c.sm_count * STREAM_SLOTS * (size_t)c.pool_mult * sizeof(PoolGame);
     const int n_groups = (grid + c.group_size - 1) / c.group_size;
     const size_t need16 = (need + 15) / 16 * 16;
     GroupState* d_groups = (GroupState*)((uint8_t*)L.d_pool + need16);

@@ -5,8 +5,8 @@
 // Why: in a player-turn only 10-45 % of the games have anything to do in a given phase, and the amount of
 // work per game is heavy-tailed, so a warp that walks the pipeline with the same 32 games issues most of its
 // instructions for 2-4 active lanes.  Here the games are REGROUPED BY PHASE:
-//   * the CTAs (one per SM, persistent) form groups of 16; every group owns a pool of 2 x 224 games per CTA in
-//     global memory (932 B each; 62 MB in total, L2-resident) and steps them until the batch's ticket counter
+//   * the CTAs (one per SM, persistent) form two groups of 74; every group owns a pool of 2 x 240 games per CTA in
+//     global memory (932 B each; 66 MB in total, L2-resident) and steps them until the batch's ticket counter
 //     runs out;
 //   * per kind of work (pipeline phases 0..14 -- with tanks/artillery/infantry and transports/subs/ships merged
 //     into one visit each --, 15 = the end-of-turn item: purchase, bookkeeping, rotation, scoring, finish +
@@ -15,13 +15,15 @@
 //     into its shared-memory slots (all 32 lanes move one game at a time: coalesced L2 loads, 4 games in
 //     flight), runs the phase on them in lockstep (engine2.cuh), copies every game back and sets its bit in the
 //     bitmap of the next phase that has work for it (per-game work mask);
-//   * the warps of a CTA serve the CTA's current kind while enough entries wait for it, so they share its few KB
-//     of instructions in the SM's instruction caches; then they move to the kind with the most entries per
-//     serving CTA.  Sixteen SMs pooling their games is what makes one kind's queue long enough for that.
+//   * a CTA is STICKY: its warps serve the CTA's current kind until one of them has found that queue empty
+//     `patience` times in a row, and only then does the CTA move to the kind with the most entries per serving
+//     CTA.  The kernel is bound by instruction delivery (the GPC-level instruction cache ran at 91 % of its request
+//     rate when CTAs changed kind every 3 batches, profiles/r2_summary.md): one CTA, one phase's few KB of code.
+//     74 SMs pooling their games is what lets every kind keep CTAs of its own.
 // No lane waits for a game of another phase, a game is only queued for phases in which it has something to
 // do, and finished pool entries restart from the ticket counter, which absorbs the long tail of game lengths.
 // The only device-wide shared word is the ticket counter; queues are per group, so claims do not contend GPU-wide
-// (a single set of device-wide queues was measured: 92 % of the time went into claim contention).
+// (a single set of device-wide FIFO queues was measured in round 1: 92 % of the time went into claim contention).
 #pragma once
 
 namespace caaa {
@@ -52,7 +54,17 @@ struct StreamShared {
   uint16_t batch[STREAM_SLOTS];   // claimed entries, LANES per warp
   uint8_t target[STREAM_SLOTS];   // the slot (lane) each claimed entry goes to
 };
-constexpr int STREAM_SMEM = TABLE_BYTES + STREAM_SLOTS * (int)sizeof(Game) + (int)((sizeof(StreamShared) + 15) / 16 * 16);
+// A pool entry / shared-memory slot: the Game padded to 936 bytes = 117 double words.  Entries and slots are then 8-byte
+// aligned, so a game moves between pool and slot with 64-bit accesses (4 per lane instead of 8: the copies are a quarter
+// of the scheduler's instructions), and 234 words per slot keeps the 16 games of a warp in 16 different banks
+// (234 j mod 32 is distinct for j < 16; an odd stride, as the 32-lane kernels use, would not be 8-byte aligned).
+struct alignas(8) PoolGame {
+  Game g;
+  uint32_t pad_;
+};
+static_assert(sizeof(PoolGame) == 936 && (sizeof(PoolGame) / 4) % 4 == 2, "slot stride: 8-byte aligned, bank-conflict free for 16 lanes");
+constexpr int POOL_DW = (int)(sizeof(PoolGame) / 8);  // 117
+constexpr int STREAM_SMEM = TABLE_BYTES + STREAM_SLOTS * (int)sizeof(PoolGame) + (int)((sizeof(StreamShared) + 15) / 16 * 16);
 static_assert(STREAM_SMEM <= 232448, "phase-regrouped kernel: shared memory budget of one sm_100a CTA");
 static_assert(MAX_GROUP * STREAM_SLOTS * MAX_POOL_MULT <= 65536 * 2 && MAX_GROUP * STREAM_SLOTS * 2 <= 65536, "pool entries are 16-bit indices at the default pool size");
 
@@ -99,7 +111,7 @@ struct StreamDbg {
 // (Re)start the pool entries of the lanes with `need_start` from the batch's ticket counter: one fetch per warp,
 // cooperative copy of the pre-imported start state.  Lanes that find no ticket left retire their entry.
 template <bool STATS>
-__device__ __noinline__ void restart_lanes(const RolloutArgs& a, Game* warp_games, Game* g, int lane, bool one_state, bool& need_start,
+__device__ __noinline__ void restart_lanes(const RolloutArgs& a, PoolGame* warp_games, Game* g, int lane, bool one_state, bool& need_start,
                                            bool& live, bool& retired, LaneTotals& tot) {
   constexpr int KW = (GAME_WORDS + 31) / 32;
   for (;;) {
@@ -116,7 +128,7 @@ __device__ __noinline__ void restart_lanes(const RolloutArgs& a, Game* warp_game
       if (gj < a.n_games) {
         const unsigned long long sj = one_state ? 0ULL : gj / a.rollouts_per_state;
         const uint32_t* src = a.templates + sj * GAME_WORDS;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + j);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&warp_games[j].g);
 #pragma unroll 1
         for (int k = 0; k < KW; k++)
           if (k * 32 + lane < GAME_WORDS) cp_async4(dst + k * 32 + lane, src + k * 32 + lane);
@@ -192,7 +204,7 @@ __device__ __forceinline__ int run_kind(int kind, Game* g, const RunCtx cx, unsi
   return res;
 }
 
-// LANES = games per warp (16: 14 warps per SM).  A warp serves ONE kind of work at a time: it claims games waiting
+// LANES = games per warp (16: 15 warps per SM).  A warp serves ONE kind of work at a time: it claims games waiting
 // for it, runs the phase on them in lockstep and routes them on.  Optionally (yield_lanes / yield_battles, off by
 // default: measured neutral) a phase yields once a share of its batch is done; the stragglers keep their loop cursor
 // in the game (engine2.cuh), are queued for the same phase again and meet other stragglers there.
@@ -202,18 +214,18 @@ template <bool STATS, int LANES, bool DBG = false>
 __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_stream(const RolloutArgs a, uint32_t* pool_all, int pool_mult,
                                                                                        GroupState* groups, int group_size, StreamDbg* dbg) {
   const DevTables* T = stage_tables(a.tables);
-  StreamShared* S = reinterpret_cast<StreamShared*>(smem_raw + TABLE_BYTES + STREAM_SLOTS * sizeof(Game));
+  StreamShared* S = reinterpret_cast<StreamShared*>(smem_raw + TABLE_BYTES + STREAM_SLOTS * sizeof(PoolGame));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int group = blockIdx.x / group_size;
   const int first_cta = group * group_size;
   const int ctas_here = ((int)gridDim.x - first_cta) < group_size ? ((int)gridDim.x - first_cta) : group_size;
   const int pool_n = STREAM_SLOTS * pool_mult * ctas_here, bm_words = pool_n / 32;
   GroupState* const GS = groups + group;
-  uint32_t* const pool = pool_all + (size_t)first_cta * STREAM_SLOTS * pool_mult * GAME_WORDS;
+  uint2* const pool = reinterpret_cast<uint2*>(pool_all) + (size_t)first_cta * STREAM_SLOTS * pool_mult * POOL_DW;
   if (threadIdx.x == 0) S->kind = -1;
   __syncthreads();
-  Game* const warp_games = reinterpret_cast<Game*>(smem_raw + TABLE_BYTES) + warp * LANES;
-  Game* const g = warp_games + (lane < LANES ? lane : 0);
+  PoolGame* const warp_games = reinterpret_cast<PoolGame*>(smem_raw + TABLE_BYTES) + warp * LANES;
+  Game* const g = &warp_games[lane < LANES ? lane : 0].g;
   uint16_t* const batch = S->batch + warp * LANES;
   const RunCtx cx{T, (uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
   const bool one_state = a.rollouts_per_state >= a.n_games;
@@ -223,7 +235,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   volatile int* vretired = &GS->retired;
   unsigned scan_rot = (unsigned)((blockIdx.x * 7 + warp * 3) * 32) % (unsigned)(((bm_words + 31) / 32) * 32);  // where this warp starts scanning
   constexpr unsigned LANE_MASK = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
-  constexpr int KW = (GAME_WORDS + 31) / 32;
+  constexpr int KD = (POOL_DW + 31) / 32;  // 64-bit accesses per lane and game
   LaneTotals tot;
   long long last_work = clock64();
   int seen_kind = -2, empty_polls = 0;
@@ -359,22 +371,22 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         __syncwarp();
         if (kind != Q_FREE) {  // copy the games in: all 32 lanes move one game at a time (coalesced), 4 games in flight
           for (int j0 = 0; j0 < n_new; j0 += 4) {
-            uint32_t r[4][KW];
+            uint2 r[4][KD];
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
               const unsigned ij = batch[(j0 + jj) < n_new ? (j0 + jj) : 0];
-              const uint32_t* src = pool + (size_t)ij * GAME_WORDS;
+              const uint2* src = pool + (size_t)ij * POOL_DW;
 #pragma unroll
-              for (int k = 0; k < KW; k++)
-                if (j0 + jj < n_new && k * 32 + lane < GAME_WORDS) r[jj][k] = __ldcg(src + k * 32 + lane);
+              for (int k = 0; k < KD; k++)
+                if (j0 + jj < n_new && k * 32 + lane < POOL_DW) r[jj][k] = __ldcg(src + k * 32 + lane);
             }
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
               const int t = S->target[warp * LANES + ((j0 + jj) < n_new ? (j0 + jj) : 0)];  // slot of the (j0+jj)-th new entry
-              uint32_t* dst = reinterpret_cast<uint32_t*>(warp_games + t);
+              uint2* dst = reinterpret_cast<uint2*>(warp_games + t);
 #pragma unroll
-              for (int k = 0; k < KW; k++)
-                if (j0 + jj < n_new && k * 32 + lane < GAME_WORDS) dst[k * 32 + lane] = r[jj][k];
+              for (int k = 0; k < KD; k++)
+                if (j0 + jj < n_new && k * 32 + lane < POOL_DW) dst[k * 32 + lane] = r[jj][k];
             }
           }
         }
@@ -423,11 +435,11 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         const int j = __ffs(mout) - 1;
         mout &= mout - 1;
         const unsigned ij = __shfl_sync(FULL, idx, j);
-        uint32_t* dst = pool + (size_t)ij * GAME_WORDS;
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(warp_games + j);
+        uint2* dst = pool + (size_t)ij * POOL_DW;
+        const uint2* src = reinterpret_cast<const uint2*>(warp_games + j);
 #pragma unroll
-        for (int k = 0; k < KW; k++)
-          if (k * 32 + lane < GAME_WORDS) __stcg(dst + k * 32 + lane, src[k * 32 + lane]);
+        for (int k = 0; k < KD; k++)
+          if (k * 32 + lane < POOL_DW) __stcg(dst + k * 32 + lane, src[k * 32 + lane]);
       }
       fence_gpu();
       __syncwarp();
