@@ -52,7 +52,6 @@ struct GroupState {
 struct StreamShared {
   int kind;                       // the phase this CTA currently serves
   uint16_t batch[STREAM_SLOTS];   // claimed entries, LANES per warp
-  uint8_t target[STREAM_SLOTS];   // the slot (lane) each claimed entry goes to
 };
 // A pool entry / shared-memory slot: the Game padded to 936 bytes = 117 double words.  Entries and slots are then 8-byte
 // aligned, so a game moves between pool and slot with 64-bit accesses (4 per lane instead of 8: the copies are a quarter
@@ -234,7 +233,6 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   volatile int* vkind = &S->kind;
   volatile int* vretired = &GS->retired;
   unsigned scan_rot = (unsigned)((blockIdx.x * 7 + warp * 3) * 32) % (unsigned)(((bm_words + 31) / 32) * 32);  // where this warp starts scanning
-  constexpr unsigned LANE_MASK = LANES == 32 ? 0xffffffffu : ((1u << LANES) - 1u);
   constexpr int KD = (POOL_DW + 31) / 32;  // 64-bit accesses per lane and game
   LaneTotals tot;
   long long last_work = clock64();
@@ -344,7 +342,6 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
     bool have = false;   // this lane holds a game of phase `kind`
     unsigned idx = 0;    // its pool entry
     {  // ---- serve `kind`: claim a batch, run it, route the games on ----
-      const unsigned free_lanes = LANE_MASK;
       const int n_new = claim(kind, LANES);
       if (n_new == 0) {
         empty_polls++;
@@ -360,13 +357,10 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
           d_items += (unsigned)n_new;
         }
         fence_gpu();
-        // the j-th new entry goes to the j-th free lane
-        const int my_rank = __popc(free_lanes & ((1u << lane) - 1u));
-        const bool got = ((free_lanes >> lane) & 1u) && my_rank < n_new;
-        if (got) {
-          idx = batch[my_rank];
+        // the j-th claimed entry goes to lane j's slot
+        if (lane < n_new) {
+          idx = batch[lane];
           have = true;
-          S->target[warp * LANES + my_rank] = (uint8_t)lane;
         }
         __syncwarp();
         if (kind != Q_FREE) {  // copy the games in: all 32 lanes move one game at a time (coalesced), 4 games in flight
@@ -382,8 +376,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
             }
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
-              const int t = S->target[warp * LANES + ((j0 + jj) < n_new ? (j0 + jj) : 0)];  // slot of the (j0+jj)-th new entry
-              uint2* dst = reinterpret_cast<uint2*>(warp_games + t);
+              uint2* dst = reinterpret_cast<uint2*>(warp_games + ((j0 + jj) < n_new ? (j0 + jj) : 0));
 #pragma unroll
               for (int k = 0; k < KD; k++)
                 if (j0 + jj < n_new && k * 32 + lane < POOL_DW) dst[k * 32 + lane] = r[jj][k];
