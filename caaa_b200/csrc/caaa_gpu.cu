@@ -263,8 +263,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) advance_kernel(const DevTables*
                                                                 int32_t* out_draws) {
   const DevTables* T = stage_tables(tables);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned m = __ballot_sync(FULL, i < n);  // the lanes of this warp that hold a state walk the pipeline in lockstep
   if (i >= n) return;
-  const unsigned m = __activemask();  // the lanes of this warp that hold a state walk the pipeline in lockstep
   Game* g = my_game();
   const RunCtx cx{T, (uint32_t)seed, (uint32_t)(seed >> 32)};
   import_state(g, states + (size_t)i * CAAA_STATE_BYTES);
@@ -282,12 +282,16 @@ namespace caaa {
 
 // Stop-at-decision mode (reference get_possible_actions / apply_action, src/engine.cpp:4050-4183).
 __device__ __forceinline__ void run_until_decision(Game* g, const RunCtx cx) {
-  for (;;) {
+  // the reference loops `while (true)` here (src/engine.cpp:4068,4135): a degenerate state in which no player ever
+  // reaches a decision would spin for ever; cap it, flag the state and report an empty action list
+  for (int turn = 0; turn < EXPAND_TURN_CAP; turn++) {
     bool stopped = false;
     for (int ph = 0; ph <= CAAA_PH_BUY_UNITS && !stopped; ph++) stopped = run_phase<true>(g, cx, ph);
     if (stopped) return;
     for (int ph = CAAA_PH_CRASH_AIR; ph < CAAA_PH_COUNT; ph++) run_phase<true>(g, cx, ph);
   }
+  g->status |= CAAA_ERR_NO_DECISION;
+  g->nvm = 0;
 }
 __device__ __forceinline__ void begin_expansion(Game* g, const RunCtx cx, int answers, int use_selected, uint8_t action) {
   begin_common(g, cx);

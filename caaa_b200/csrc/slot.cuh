@@ -122,7 +122,9 @@ struct DevTables {
 enum : uint32_t {
   CAAA_ERR_SEA_ROUND_CAP = 1u,   // a sea battle exceeded SEA_ROUND_CAP rounds (the reference would never return)
   CAAA_ERR_LOAD_FAILED = 2u,     // load_transport found no transport (the reference prints and loops)
+  CAAA_ERR_NO_DECISION = 4u,     // expansion mode: no player reached a decision within EXPAND_TURN_CAP turns (the reference would spin)
 };
+constexpr int EXPAND_TURN_CAP = 5000;
 constexpr int SEA_ROUND_CAP = 10000;
 
 static_assert(sizeof(CaaaGameState) == 670, "GameState layout");

@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
   LaneTotals tot;
   long long last_work = clock64();
   int seen_kind = -2, empty_polls = 0;
+  bool was_idle = false;
   unsigned long long d_batches = 0, d_items = 0, d_t[6] = {0, 0, 0, 0, 0, 0};
   long long d_c0 = clock64();
 #define CAAA_LAP(k)                                   \
@@ -314,9 +315,13 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       const unsigned key = __reduce_max_sync(FULL, score ? (score << 5) | (unsigned)lane : 0u);
       if (key == 0) {
         if (*vretired >= pool_n) break;  // every pool entry has retired: the batch is done
-        // watchdog: games are left but nothing has been claimable for ~4 s -- give up rather than hang the GPU;
+        // watchdog: games are left but NO queue of the group has held an entry for ~4 s without interruption -- give up rather than hang the GPU;
         // the host reports the failure (it would mean a lost pool entry, i.e. a bug in this scheduler)
         if (*reinterpret_cast<volatile int*>(&GS->aborted)) break;
+        if (!was_idle) {  // the clock runs from the moment the queues were first seen empty, not from this warp's last claim
+          was_idle = true;
+          last_work = clock64();
+        }
         if (clock64() - last_work > 8000000000LL) {
           if (lane == 0) {
             atomicExch(&GS->aborted, 1);
@@ -327,6 +332,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         __nanosleep(200);
         continue;
       }
+      was_idle = false;
       const int nk = (int)(key & 31u);
       if (lane == 0) {
         const int old = atomicExch(&S->kind, nk);  // several warps may switch at once: account for the change once
