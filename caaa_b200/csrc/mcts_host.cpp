@@ -10,7 +10,10 @@
 // virtual visits, and two such batches are kept in flight so one host thread keeps the GPU busy.  With both set to 1 the loop is
 // the reference's, except that is_terminal_state is evaluated on the node's own unit totals (the
 // reference reads stale globals there) and the random stream is Philox.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <deque>
@@ -104,6 +107,9 @@ extern "C" int caaa_mcts_search_pipelined(const CaaaGameState* root_state, int64
   if (depth > 1 && caaa_gpu_device_info(&sm_count, nullptr, nullptr) == CAAA_OK && sm_count > 32)
     caaa_gpu_set_rollout_sms((sm_count - 4) / 16 * 16);  // a few SMs stay free for the other batch's expansion kernels
   int rc = CAAA_OK;
+  const bool trace = std::getenv("CAAA_MCTS_TRACE") != nullptr;  // per-batch host timeline on stderr
+  const auto t_start = std::chrono::steady_clock::now();
+  auto ms_now = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count(); };
   while (rc == CAAA_OK && (selected < iterations || !flights.empty())) {
     // 1. keep `depth` batches in flight: select distinct leaves, marking virtual visits along their paths
     while (!free_handles.empty() && selected < iterations) {
@@ -125,6 +131,7 @@ extern "C" int caaa_mcts_search_pipelined(const CaaaGameState* root_state, int64
         picks[i] = rng();  // `rand() % num_children`, reference src/mcts.cpp:86 (the modulo is taken on the device)
       }
       f.handle = free_handles.back();
+      if (trace) std::fprintf(stderr, "mcts %9.2f ms  submit  handle %d  %d leaves\n", ms_now(), f.handle, nl);
       rc = caaa_gpu_leaf_batch_submit(f.handle, states.data(), nl, rollouts_per_leaf, seed, next_game_id, picks.data());
       if (rc != CAAA_OK) break;
       free_handles.pop_back();
@@ -144,8 +151,10 @@ extern "C" int caaa_mcts_search_pipelined(const CaaaGameState* root_state, int64
     children.resize((size_t)nl * CAAA_ACTIONS);
     status.resize(nl);
     picked.resize(nl);
+    if (trace) std::fprintf(stderr, "mcts %9.2f ms  wait    handle %d\n", ms_now(), f.handle);
     rc = caaa_gpu_leaf_batch_collect(f.handle, scores.data(), n_actions.data(), actions.data(), children.data(), status.data(),
                                      picked.data(), sums.data(), nullptr);
+    if (trace) std::fprintf(stderr, "mcts %9.2f ms  collect handle %d  %d leaves\n", ms_now(), f.handle, nl);
     free_handles.push_back(f.handle);
     if (rc != CAAA_OK) break;
     for (int i = 0; i < nl; i++) {
