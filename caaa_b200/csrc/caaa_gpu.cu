@@ -69,6 +69,7 @@ struct RolloutArgs {
   int min_batch_polls;
   unsigned idle_ns;     // sleep of an idle warp between two looks at the queues
   int* abort_flag;      // set when the watchdog gave up (global memory, optional)
+  int bucket_land, bucket_sea, bucket_money;  // pool kernel: thresholds of the work-size buckets (a huge value switches one off)
   int patience;         // pool kernel: empty claims in a row before a CTA leaves its phase (0 = round 1's queue-length rule)
 };
 
@@ -627,6 +628,9 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.idle_ns = (unsigned)env_int("CAAA_IDLE_NS", 100);
   a.abort_flag = L.d_abort;
   a.patience = env_int("CAAA_PATIENCE", 6);
+  a.bucket_land = env_int("CAAA_BUCKET_LAND", 6);
+  a.bucket_sea = env_int("CAAA_BUCKET_SEA", 8);
+  a.bucket_money = env_int("CAAA_BUCKET_MONEY", 15);
   if (a.patience < 1) a.patience = 1;
   {  // which kernel: CAAA_ROLLOUT_KERNEL = resident | stream | lockstep forces one; default = by batch size
     const char* rk = std::getenv("CAAA_ROLLOUT_KERNEL");

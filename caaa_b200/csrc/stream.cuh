@@ -28,9 +28,16 @@
 
 namespace caaa {
 
-constexpr int NQ = 17;                   // phases 0..14, 15 = end of turn (purchase, bookkeeping, rotation, scoring,
+constexpr int NQ = 20;                   // phases 0..14, 15 = end of turn (purchase, bookkeeping, rotation, scoring,
 constexpr int Q_EOT = CAAA_PH_BUY_UNITS; // finish + restart), 16 = free pool entries
 constexpr int Q_FREE = 16;
+// Work-size buckets: the three heaviest kinds have a second queue for games that are expected to need many decision steps
+// (many movable units / much money), so that a batch -- which runs as long as its longest game -- is formed from games of
+// similar length.  The code a CTA runs for a heavy queue is that of the base kind.
+constexpr int Q_LAND_HEAVY = 17, Q_SEA_HEAVY = 18, Q_EOT_HEAVY = 19;
+__device__ __forceinline__ int base_kind(int q) {
+  return q == Q_LAND_HEAVY ? (int)CAAA_PH_MOVE_TANKS : q == Q_SEA_HEAVY ? (int)CAAA_PH_MOVE_TRANSPORTS : q == Q_EOT_HEAVY ? Q_EOT : q;
+}
 constexpr int STREAM_SLOTS = 240;        // shared-memory game slots per CTA: 15 warps x 16 games, all of the 227 KB
 constexpr int MAX_POOL_MULT = 4;
 constexpr int MAX_BM_WORDS = STREAM_SLOTS * MAX_POOL_MULT / 32;  // 28 bitmap words per phase
@@ -355,6 +362,8 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         continue;
       }
       empty_polls = 0;
+      const int queue = kind;  // the queue the batch came from; `kind` is the code that runs on it
+      kind = base_kind(queue);
       CAAA_LAP(0);  // idle + select + claim
       if (n_new > 0) {
         last_work = clock64();
@@ -406,8 +415,8 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       if (runs) res = run_kind<STATS>(kind, g, cx, mhave, yield, a, tot, live, need_start);
       __syncwarp();
       if (DBG && lane == 0) {
-        atomicAdd(&dbg->kind_cycles[kind], (unsigned long long)(clock64() - d_c0));
-        atomicAdd(&dbg->kind_items[kind], (unsigned long long)n_new);
+        atomicAdd(&dbg->kind_cycles[queue], (unsigned long long)(clock64() - d_c0));
+        atomicAdd(&dbg->kind_items[queue], (unsigned long long)n_new);
       }
       CAAA_LAP(2);  // compute
       // ---- (re)start pool entries from the ticket counter (out of line: it runs once per playout, and the hot loop of
@@ -419,7 +428,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       // yielded stay in their slots ----
       int nxt = -1;
       if (runs && live && res == PH_YIELDED) {
-        nxt = kind;
+        nxt = queue;
       } else if (runs && live) {
         uint32_t w = g->work & W_ALL_MOVES;
         const int last = kind == CAAA_PH_MOVE_TANKS ? (int)CAAA_PH_MOVE_INFANTRY : kind == CAAA_PH_MOVE_TRANSPORTS ? (int)CAAA_PH_MOVE_SHIPS : kind;
@@ -427,6 +436,23 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
         nxt = w ? __ffs(w) - 1 : Q_EOT;
         if (nxt == CAAA_PH_MOVE_ARTILLERY || nxt == CAAA_PH_MOVE_INFANTRY) nxt = CAAA_PH_MOVE_TANKS;  // the merged land mover
         if (nxt == CAAA_PH_MOVE_SUBS || nxt == CAAA_PH_MOVE_SHIPS) nxt = CAAA_PH_MOVE_TRANSPORTS;      // the merged sea mover
+        {  // expected work of the next visit -> light or heavy queue of that kind (a sea-battle bucket by units engaged
+           // was measured too: no gain)
+          const int cur = g->cur;
+          if (nxt == CAAA_PH_MOVE_TANKS) {
+            int n = 0;
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+              const uint8_t* r = g->lu[l];
+              n += r[off_lu(TANKS) + 1] + r[off_lu(TANKS) + 2] + r[off_lu(ARTILLERY) + 1] + r[off_lu(INFANTRY) + 1];
+            }
+            if (n > a.bucket_land) nxt = Q_LAND_HEAVY;
+          } else if (nxt == CAAA_PH_MOVE_TRANSPORTS) {
+            if (g->tot_sea[cur][0] + g->tot_sea[cur][1] + g->tot_sea[cur][2] > a.bucket_sea) nxt = Q_SEA_HEAVY;
+          } else if (nxt == Q_EOT) {
+            if (g->money[cur] > a.bucket_money) nxt = Q_EOT_HEAVY;
+          }
+        }
       }
       unsigned mout = __ballot_sync(FULL, nxt >= 0);
       __syncwarp();
