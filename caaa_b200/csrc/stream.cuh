@@ -19,7 +19,9 @@
 //     `patience` times in a row, and only then does the CTA move to the kind with the most entries per serving
 //     CTA.  The kernel is bound by instruction delivery (the GPC-level instruction cache ran at 91 % of its request
 //     rate when CTAs changed kind every 3 batches, profiles/r2_summary.md): one CTA, one phase's few KB of code.
-//     74 SMs pooling their games is what lets every kind keep CTAs of its own.
+//     74 SMs pooling their games is what lets every kind keep CTAs of its own;
+//   * the three heaviest kinds have a second, "heavy" queue (work-size buckets, see Q_LAND_HEAVY below): a batch runs as
+//     long as its longest game, so it should be formed from games of similar length.
 // No lane waits for a game of another phase, a game is only queued for phases in which it has something to
 // do, and finished pool entries restart from the ticket counter, which absorbs the long tail of game lengths.
 // The only device-wide shared word is the ticket counter; queues are per group, so claims do not contend GPU-wide
