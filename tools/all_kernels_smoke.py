@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Small invocations of every kernel for `compute-sanitizer --tool memcheck` (tools; not part of the product)."""
+"""Small invocations of every kernel through the C-ABI (tools; not part of the product): a quick all-kernels smoke run.
+(Written for `compute-sanitizer --tool memcheck`, which is closed on this GPU pool.)"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

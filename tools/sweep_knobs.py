@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""Knob sweep of the SM-resident rollout kernel (tools; not part of the product).
+"""Knob sweep of the rollout kernels (tools; not part of the product).
 
-    python tools/sweep_resident.py [playouts] [spec ...]     spec = "CAAA_WARPS=24,CAAA_YIELD=50"
+    python tools/sweep_knobs.py [playouts] [spec ...]     spec = "CAAA_PATIENCE=8,CAAA_BUCKET_MONEY=12"
 
 One process; the library reads its knobs from the environment at every launch.  Kernel time comes from
 the library's own CUDA events (CaaaBatchSummary.kernel_ms) around the launch.
