@@ -728,11 +728,13 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
                    h.batches, h.batches ? (double)h.items / (double)h.batches : 0.0, h.t[0] / tt, h.t[1] / tt, h.t[2] / tt, h.t[3] / tt,
                    h.t[4] / tt, tt / (grid * (STREAM_SLOTS / c.lanes)) / 1e6);
       std::fprintf(stderr, "stream dbg: CTA kind switches %llu = one per %.1f batches of the CTA\n", h.t[5], h.t[5] ? (double)h.batches / (double)h.t[5] : 0.0);
-      std::fprintf(stderr, "stream dbg: per kind  share of phase time / share of game visits:");
+      std::fprintf(stderr, "stream dbg: per queue  share of phase time / share of game visits / games per batch:");
       double kc = 0, ki = 0;
       for (int q = 0; q < NQ; q++) { kc += (double)h.kind_cycles[q]; ki += (double)h.kind_items[q]; }
       for (int q = 0; q < NQ; q++)
-        if (h.kind_items[q]) std::fprintf(stderr, "  k%d %.3f/%.3f", q, h.kind_cycles[q] / kc, h.kind_items[q] / ki);
+        if (h.kind_items[q])
+          std::fprintf(stderr, "  k%d %.3f/%.3f/%.1f", q, h.kind_cycles[q] / kc, h.kind_items[q] / ki,
+                       (double)h.kind_items[q] / (double)(h.kind_batches[q] ? h.kind_batches[q] : 1));
       std::fprintf(stderr, "\n");
     }
   } else if (c.sync_phases) {

@@ -113,7 +113,7 @@ __device__ __forceinline__ unsigned long long ld_vol_u64(const unsigned long lon
 
 struct StreamDbg {
   unsigned long long batches, items, t[6];
-  unsigned long long kind_cycles[NQ], kind_items[NQ];  // phase-code time and games per kind of work
+  unsigned long long kind_cycles[NQ], kind_items[NQ], kind_batches[NQ];  // phase-code time, games and batches per queue
 };
 
 // (Re)start the pool entries of the lanes with `need_start` from the batch's ticket counter: one fetch per warp,
@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(STREAM_SLOTS / LANES * 32, 1) rollout_kernel_s
       if (DBG && lane == 0) {
         atomicAdd(&dbg->kind_cycles[queue], (unsigned long long)(clock64() - d_c0));
         atomicAdd(&dbg->kind_items[queue], (unsigned long long)n_new);
+        atomicAdd(&dbg->kind_batches[queue], 1ULL);
       }
       CAAA_LAP(2);  // compute
       // ---- (re)start pool entries from the ticket counter (out of line: it runs once per playout, and the hot loop of
