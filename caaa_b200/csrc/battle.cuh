@@ -27,7 +27,7 @@ static_assert(BATTLE_SMEM <= 232448, "battle kernel: shared memory budget");
 __global__ void __launch_bounds__(BATTLE_WARPS * 32, 1) battle_kernel(const DevTables* tables, const uint8_t* states, int n,
                                                                       unsigned long long seed, unsigned long long first_game_id,
                                                                       uint8_t* out_states, int32_t* out_draws, CaaaBatchSummary* summary,
-                                                                      unsigned int* work_counter, int run) {
+                                                                      unsigned int* work_counter, int run, int yield_div) {
   const DevTables* T = stage_tables(tables);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* const wbase = smem_raw + TABLE_BYTES + warp * BATTLE_WARP_BYTES;
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(BATTLE_WARPS * 32, 1) battle_kernel(const DevT
     const unsigned msea = __ballot_sync(FULL, stage == 1);
     if (msea) {
       if (stage == 1) {
-        const int y = exhausted && next >= run_end ? 0 : (__popc(msea) + 3) / 4;  // nothing left to refill with: run to the end
+        const int y = exhausted && next >= run_end ? 0 : (__popc(msea) + yield_div - 1) / yield_div;  // nothing left to refill with: run to the end
         if (resolve_sea_battles<false>(g, cx, msea, y) != PH_YIELDED) stage = 2;
       }
       __syncwarp();
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(BATTLE_WARPS * 32, 1) battle_kernel(const DevT
     const unsigned mland = __ballot_sync(FULL, stage == 2);
     if (mland) {
       if (stage == 2) {
-        const int y = exhausted && next >= run_end ? 0 : (__popc(mland) + 3) / 4;
+        const int y = exhausted && next >= run_end ? 0 : (__popc(mland) + yield_div - 1) / yield_div;
         if (resolve_land_battles<false>(g, cx, mland, y) != PH_YIELDED) stage = 3;
       }
       __syncwarp();

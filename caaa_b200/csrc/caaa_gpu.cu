@@ -1037,9 +1037,12 @@ static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t f
   const int want = (n + run - 1) / run;  // warps that can get a run at all
   int grid = (want + BATTLE_WARPS - 1) / BATTLE_WARPS;
   if (grid > c.sm_count) grid = c.sm_count;
+  const char* yd = std::getenv("CAAA_BATTLE_YIELD_DIV");  // a phase yields once 1/yield_div of its lanes are done
+  int yield_div = yd ? std::atoi(yd) : 4;
+  if (yield_div < 1) yield_div = 1;
   CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
   battle_kernel<<<grid, BATTLE_WARPS * 32, BATTLE_SMEM, stream>>>(c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id,
-                                                                  (uint8_t*)d_out, d_draws, d_summary, d_counter, run);
+                                                                  (uint8_t*)d_out, d_draws, d_summary, d_counter, run, yield_div);
   CUDA_TRY(cudaGetLastError());
   return CAAA_OK;
 }
