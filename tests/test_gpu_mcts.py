@@ -77,6 +77,26 @@ def test_pipelined_search_is_deterministic_and_complete(eng):
     assert v.sum() == 400 and info["nodes"] > 400
 
 
+def test_root_visit_shares_match_the_reference_search(eng):
+    """The GPU-backed search against the reference's own `mcts_search` (src/mcts.cpp:65-108): 20 000 iterations from the
+    start position, one rollout per visited leaf.  The two searches draw from different random streams (glibc `rand()` and
+    its byte table there, mt19937 + Philox here) and the GPU one selects 128 leaves per batch with virtual visits, so only
+    the statistics can agree: the share of root visits per action stays within 0.08 of the reference's known answer
+    (reproduced exactly by tests/test_oracle_vs_ref.py), the two weak openings (actions 6 and 0:
+    saving everything, buying nothing useful) are starved of visits by both, and the best action is one of the
+    reference's two best (4 at 20 000 iterations, 2 at 100 000)."""
+    from caaa_b200 import host
+    ref = np.array([892, 4664, 5166, 3693, 5054, 531], dtype=np.float64) / 20000.0
+    a, v, x, best, info = host.mcts_search(eng, layout.start_state(), 20000, 1, 128, seed=4)
+    assert a.tolist() == [6, 5, 4, 3, 2, 0] and v.sum() == 20000
+    share = v / v.sum()
+    assert np.abs(share - ref).max() < 0.08, (share, ref)
+    assert share[0] < 0.08 and share[5] < 0.08 and (share[1:5] > 0.15).all()
+    assert best in (2, 4, 5, 3)
+    means = x / np.maximum(v, 1)
+    assert means[1:5].min() > means[0] and means[1:5].min() > means[5]   # both searches rank the weak openings last
+
+
 def test_root_parallel_two_ranks_real_search(tmp_path):
     """BASELINE config 5 at world size 2 with the REAL search on two GPUs: the statistics all-reduced by
     caaa_root_allreduce (NCCL) equal the host-side sum of the per-rank statistics."""
