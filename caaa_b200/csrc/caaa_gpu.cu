@@ -474,6 +474,7 @@ struct LeafBatch {
 };
 struct Context {
   bool ready = false;
+  CaaaMap map;
   BattlePipe battle;
   unsigned int* d_battle_counters = nullptr;  // work counters of the battle kernel: one per pipeline buffer + four for device launches
   unsigned next_battle_counter = 0;
@@ -756,9 +757,34 @@ extern "C" {
 
 const char* caaa_gpu_last_error(void) { return g_err.c_str(); }
 
+int caaa_gpu_default_map(CaaaMap* out) {
+  if (!out) return fail(CAAA_E_ARG, "null argument");
+  default_map(out);
+  return CAAA_OK;
+}
+
+int caaa_gpu_tables_for_map(const CaaaMap* map, CaaaTables* out) {
+  if (!map || !out) return fail(CAAA_E_ARG, "null argument");
+  if (!valid_map(*map)) return fail(CAAA_E_ARG, "invalid map: an index out of range or more neighbours than the tables hold");
+  build_tables(*map, out);
+  return CAAA_OK;
+}
+
 int caaa_gpu_init(int device) {
+  CaaaMap m;
+  default_map(&m);
+  return caaa_gpu_init_map(device, &m);
+}
+
+int caaa_gpu_init_map(int device, const CaaaMap* map) {
   Context& c = g_ctx;
-  if (c.ready) return CAAA_OK;
+  if (!map) return fail(CAAA_E_ARG, "null argument");
+  if (!valid_map(*map)) return fail(CAAA_E_ARG, "invalid map: an index out of range or more neighbours than the tables hold");
+  if (c.ready) {
+    if (std::memcmp(&c.map, map, sizeof(CaaaMap)) == 0) return CAAA_OK;
+    return fail(CAAA_E_ARG, "the library is already initialised with another map: call caaa_gpu_shutdown() first");
+  }
+  c.map = *map;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) return fail(CAAA_E_NO_DEVICE, "no CUDA device available (this library has no CPU path)", e);
@@ -770,7 +796,7 @@ int caaa_gpu_init(int device) {
     return fail(CAAA_E_NO_DEVICE, "device does not offer 227 KB of shared memory per block (built for sm_100a)");
   c.device = device;
   c.sm_count = prop.multiProcessorCount;
-  build_dev_tables(&c.host_tables);
+  build_dev_tables(c.map, &c.host_tables);
   CUDA_TRY(cudaMalloc(&c.d_tables, sizeof(DevTables)));
   CUDA_TRY(cudaMemcpy(c.d_tables, &c.host_tables, sizeof(DevTables), cudaMemcpyHostToDevice));
   for (LaunchSlot& l : c.slots) {
@@ -898,7 +924,11 @@ int caaa_gpu_shutdown(void) {
 
 int caaa_gpu_get_tables(CaaaTables* out) {
   if (!out) return fail(CAAA_E_ARG, "null argument");
-  build_tables(out);  // host computation; identical to what caaa_gpu_init uploads
+  // host computation; identical to what caaa_gpu_init uploads (the map the library was initialised with, else the default)
+  CaaaMap m;
+  if (g_ctx.ready) m = g_ctx.map;
+  else default_map(&m);
+  build_tables(m, out);
   return CAAA_OK;
 }
 

@@ -13,7 +13,7 @@
 namespace caaa {
 namespace {
 
-// reference src/land.cpp:4-20, src/sea.cpp:5-8, src/canal.cpp:3-6, src/player.cpp:9-13
+// reference src/land.cpp:4-20, src/sea.cpp:5-8, src/canal.cpp:3-6, src/player.cpp:9-13: the default board
 struct LandDef { uint8_t owner, value; uint8_t n_sea; uint8_t sea[4]; uint8_t n_land; uint8_t land[6]; };
 struct SeaDef { uint8_t n_sea; uint8_t sea[7]; uint8_t n_land; uint8_t land[6]; };
 constexpr LandDef kLands[NL] = {
@@ -46,30 +46,85 @@ void relax_u8(uint8_t (&d)[ROWS][COLS], int n_mid) {
 
 }  // namespace
 
-void build_tables(CaaaTables* out) {
-  CaaaTables& t = *out;
-  std::memset(&t, 0, sizeof(t));
+void default_map(CaaaMap* out) {
+  CaaaMap& m = *out;
+  std::memset(&m, 0, sizeof(m));
   for (int l = 0; l < NL; l++) {
     const LandDef& L = kLands[l];
-    t.land_value[l] = L.value;
-    t.original_owner[l] = L.owner;
-    t.l2l_count[l] = L.n_land;
-    t.l2s_count[l] = L.n_sea;
-    std::memcpy(t.l2l_conn[l], L.land, L.n_land);
-    std::memcpy(t.l2s_conn[l], L.sea, L.n_sea);
+    m.land_owner[l] = L.owner;
+    m.land_value[l] = L.value;
+    m.land_sea_count[l] = L.n_sea;
+    m.land_land_count[l] = L.n_land;
+    std::memcpy(m.land_sea[l], L.sea, L.n_sea);
+    std::memcpy(m.land_land[l], L.land, L.n_land);
   }
   for (int s = 0; s < NS; s++) {
     const SeaDef& S = kSeas[s];
-    t.s2s_count[s] = S.n_sea;
-    t.s2l_count[s] = S.n_land;
-    std::memcpy(t.s2s_conn[s], S.sea, S.n_sea);
-    std::memcpy(t.s2l_conn[s], S.land, S.n_land);
+    m.sea_sea_count[s] = S.n_sea;
+    m.sea_land_count[s] = S.n_land;
+    std::memcpy(m.sea_sea[s], S.sea, S.n_sea);
+    std::memcpy(m.sea_land[s], S.land, S.n_land);
+  }
+  std::memcpy(m.canal_seas, kCanalSeas, sizeof(kCanalSeas));
+  std::memcpy(m.canal_lands, kCanalLands, sizeof(kCanalLands));
+  for (int p = 0; p < NP; p++) {
+    m.capital[p] = kCapital[p];
+    for (int q = 0; q < NP; q++) m.is_allied[p][q] = kAxis[p] == kAxis[q];
+  }
+}
+
+bool valid_map(const CaaaMap& m) {
+  for (int l = 0; l < NL; l++) {
+    if (m.land_owner[l] >= NP || m.land_sea_count[l] > 4 || m.land_land_count[l] > 6) return false;
+    // a land has at most NL - 1 land and NS sea neighbours, an air location at most 7 (air_conn[8][7])
+    if (m.land_land_count[l] > NL - 1 || m.land_sea_count[l] > NS || m.land_land_count[l] + m.land_sea_count[l] > 7) return false;
+    for (int i = 0; i < m.land_sea_count[l]; i++)
+      if (m.land_sea[l][i] >= NS) return false;
+    for (int i = 0; i < m.land_land_count[l]; i++)
+      if (m.land_land[l][i] >= NL || m.land_land[l][i] == l) return false;
+  }
+  for (int s = 0; s < NS; s++) {
+    if (m.sea_sea_count[s] > NS - 1 || m.sea_land_count[s] > NL || m.sea_sea_count[s] + m.sea_land_count[s] > 7) return false;
+    for (int i = 0; i < m.sea_sea_count[s]; i++)
+      if (m.sea_sea[s][i] >= NS || m.sea_sea[s][i] == s) return false;
+    for (int i = 0; i < m.sea_land_count[s]; i++)
+      if (m.sea_land[s][i] >= NL) return false;
+  }
+  for (int k = 0; k < CAAA_CANALS; k++)
+    if (m.canal_seas[k][0] >= NS || m.canal_seas[k][1] >= NS || m.canal_lands[k][0] >= NL || m.canal_lands[k][1] >= NL) return false;
+  for (int p = 0; p < NP; p++) {
+    if (m.capital[p] >= NL || !m.is_allied[p][p]) return false;
+    for (int q = 0; q < NP; q++)
+      if (m.is_allied[p][q] > 1 || m.is_allied[p][q] != m.is_allied[q][p]) return false;
+    int enemies = 0;
+    for (int q = 0; q < NP; q++) enemies += !m.is_allied[p][q];
+    if (enemies > 4) return false;
+  }
+  return true;
+}
+
+void build_tables(const CaaaMap& m, CaaaTables* out) {
+  CaaaTables& t = *out;
+  std::memset(&t, 0, sizeof(t));
+  for (int l = 0; l < NL; l++) {
+    t.land_value[l] = m.land_value[l];
+    t.original_owner[l] = m.land_owner[l];
+    t.l2l_count[l] = m.land_land_count[l];
+    t.l2s_count[l] = m.land_sea_count[l];
+    std::memcpy(t.l2l_conn[l], m.land_land[l], m.land_land_count[l]);
+    std::memcpy(t.l2s_conn[l], m.land_sea[l], m.land_sea_count[l]);
+  }
+  for (int s = 0; s < NS; s++) {
+    t.s2s_count[s] = m.sea_sea_count[s];
+    t.s2l_count[s] = m.sea_land_count[s];
+    std::memcpy(t.s2s_conn[s], m.sea_sea[s], m.sea_sea_count[s]);
+    std::memcpy(t.s2l_conn[s], m.sea_land[s], m.sea_land_count[s]);
   }
   for (int p = 0; p < NP; p++) {
-    t.capital[p] = kCapital[p];
-    for (int q = 0; q < NP; q++) t.is_allied[p][q] = kAxis[p] == kAxis[q];
+    t.capital[p] = m.capital[p];
+    for (int q = 0; q < NP; q++) t.is_allied[p][q] = m.is_allied[p][q];
   }
-  std::memcpy(t.canal_lands, kCanalLands, sizeof(kCanalLands));
+  std::memcpy(t.canal_lands, m.canal_lands, sizeof(m.canal_lands));
 
   // distances: start at 255, own territory 0, neighbours 1, then relax (engine.cpp:179-377)
   std::memset(t.land_dist, 0xff, sizeof(t.land_dist));
@@ -87,7 +142,7 @@ void build_tables(CaaaTables* out) {
       for (int i = 0; i < t.s2s_count[s]; i++) t.sea_dist[c][s][t.s2s_conn[s][i]] = t.sea_dist[c][t.s2s_conn[s][i]][s] = 1;
     }
     for (int k = 0; k < CAAA_CANALS; k++)
-      if (c & (1 << k)) t.sea_dist[c][kCanalSeas[k][0]][kCanalSeas[k][1]] = t.sea_dist[c][kCanalSeas[k][1]][kCanalSeas[k][0]] = 1;
+      if (c & (1 << k)) t.sea_dist[c][m.canal_seas[k][0]][m.canal_seas[k][1]] = t.sea_dist[c][m.canal_seas[k][1]][m.canal_seas[k][0]] = 1;
     relax_u8(t.sea_dist[c], NS);
   }
   auto air_edge = [&t](int a, int b) {
@@ -154,9 +209,9 @@ void build_tables(CaaaTables* out) {
     }
 }
 
-void build_dev_tables(DevTables* out) {
+void build_dev_tables(const CaaaMap& m, DevTables* out) {
   std::memset(out, 0, sizeof(*out));
-  build_tables(&out->t);
+  build_tables(m, &out->t);
   for (uint32_t n = 1; n < 32; n++) out->recip16[n] = 65536u / n + 1u;
   {  // cell lists of the move phases (reference loop orders, src/engine.cpp:1593-1599, 1734, 1998, 2088-2098, ...)
     using e2::Game;

@@ -3,6 +3,8 @@
 #include "slot.cuh"
 
 namespace caaa {
-void build_tables(CaaaTables* out);      // reference initialize_constants(), src/engine.cpp:165-513
-void build_dev_tables(DevTables* out);   // + per-player team lists (refresh_allies, 716-725)
+void default_map(CaaaMap* out);                              // the reference's compiled-in board (src/land.cpp, sea.cpp, canal.cpp, player.cpp)
+bool valid_map(const CaaaMap& m);                            // indices in range, counts within the table capacities
+void build_tables(const CaaaMap& m, CaaaTables* out);        // reference initialize_constants(), src/engine.cpp:165-513
+void build_dev_tables(const CaaaMap& m, DevTables* out);     // + per-player team lists (refresh_allies, 716-725)
 }  // namespace caaa

@@ -4,12 +4,12 @@ import os
 
 import numpy as np
 
-from .layout import CACHE_DTYPE, STATE_BYTES, STATS_DTYPE, SUMMARY_DTYPE, TABLES_DTYPE
+from .layout import CACHE_DTYPE, MAP_DTYPE, STATE_BYTES, STATS_DTYPE, SUMMARY_DTYPE, TABLES_DTYPE
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libcaaa_gpu.so")
 
 # every symbol include/caaa_gpu.h declares
-SYMBOLS = ["caaa_gpu_init", "caaa_gpu_shutdown", "caaa_gpu_last_error", "caaa_gpu_get_tables",
+SYMBOLS = ["caaa_gpu_init", "caaa_gpu_init_map", "caaa_gpu_default_map", "caaa_gpu_tables_for_map", "caaa_gpu_shutdown", "caaa_gpu_last_error", "caaa_gpu_get_tables",
            "caaa_gpu_device_info", "caaa_gpu_rollout_batch", "caaa_gpu_rollout_batch_device",
            "caaa_gpu_synchronize", "caaa_gpu_set_stream", "caaa_gpu_random_play_until_terminal", "caaa_gpu_advance",
            "caaa_gpu_resolve_battles", "caaa_gpu_resolve_battles_device", "caaa_gpu_expand", "caaa_gpu_evaluate",
@@ -32,6 +32,9 @@ def load_library(path=LIB_PATH):
     lib = C.CDLL(path)
     vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
     lib.caaa_gpu_init.argtypes = [i32]
+    lib.caaa_gpu_init_map.argtypes = [i32, vp]
+    lib.caaa_gpu_default_map.argtypes = [vp]
+    lib.caaa_gpu_tables_for_map.argtypes = [vp, vp]
     lib.caaa_gpu_last_error.restype = C.c_char_p
     lib.caaa_gpu_get_tables.argtypes = [vp]
     lib.caaa_gpu_device_info.argtypes = [vp, vp, vp]
@@ -68,12 +71,39 @@ def _states(a):
     return a
 
 
+def default_map(lib=None):
+    """The reference's compiled-in board as a CaaaMap record (host only; no GPU needed)."""
+    lib = lib or load_library()
+    m = np.zeros(1, dtype=MAP_DTYPE)
+    if lib.caaa_gpu_default_map(m.ctypes.data) != 0:
+        raise CaaaGpuError("caaa_gpu_default_map failed")
+    return m[0]
+
+
+def tables_for_map(game_map, lib=None):
+    """initialize_constants() for a board (host only); raises on an invalid map."""
+    lib = lib or load_library()
+    m = np.ascontiguousarray(game_map)
+    t = np.zeros(1, dtype=TABLES_DTYPE)
+    rc = lib.caaa_gpu_tables_for_map(m.ctypes.data, t.ctypes.data)
+    if rc != 0:
+        raise CaaaGpuError(f"caaa_gpu_tables_for_map error {rc}: {lib.caaa_gpu_last_error().decode()}")
+    return t[0]
+
+
 class GpuEngine:
     """One context per process (the library keeps one context per device)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, game_map=None):
         self.lib = load_library()
-        self._check(self.lib.caaa_gpu_init(device))
+        if game_map is None:
+            self._check(self.lib.caaa_gpu_init(device))
+        else:
+            m = np.ascontiguousarray(game_map)
+            self._check(self.lib.caaa_gpu_init_map(device, m.ctypes.data))
+
+    def shutdown(self):
+        self._check(self.lib.caaa_gpu_shutdown())
 
     def _check(self, rc):
         if rc != 0:

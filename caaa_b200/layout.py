@@ -50,6 +50,36 @@ TABLES_DTYPE = np.dtype([
     ("air_to_land_within_count", "u1", (6, 8)), ("air_to_land_within", "u1", (6, 8, 5))])
 
 
+MAP_DTYPE = np.dtype([
+    ("land_owner", "u1", (5,)), ("land_value", "u1", (5,)), ("land_sea_count", "u1", (5,)), ("land_land_count", "u1", (5,)),
+    ("land_sea", "u1", (5, 4)), ("land_land", "u1", (5, 6)), ("sea_sea_count", "u1", (3,)), ("sea_land_count", "u1", (3,)),
+    ("sea_sea", "u1", (3, 7)), ("sea_land", "u1", (3, 6)), ("canal_seas", "u1", (2, 2)), ("canal_lands", "u1", (2, 2)),
+    ("capital", "u1", (5,)), ("is_allied", "u1", (5, 5))])
+
+
+def map_from_json(path):
+    """A board description (tests/golden/alt_map.json shows the format) as a CaaaMap record."""
+    import json
+    with open(path) as f:
+        d = json.load(f)
+    m = np.zeros((), dtype=MAP_DTYPE)
+    for i, land in enumerate(d["lands"]):
+        m["land_owner"][i], m["land_value"][i] = land["owner"], land["value"]
+        m["land_sea_count"][i], m["land_land_count"][i] = len(land["seas"]), len(land["lands"])
+        m["land_sea"][i][:len(land["seas"])] = land["seas"]
+        m["land_land"][i][:len(land["lands"])] = land["lands"]
+    for i, sea in enumerate(d["seas"]):
+        m["sea_sea_count"][i], m["sea_land_count"][i] = len(sea["seas"]), len(sea["lands"])
+        m["sea_sea"][i][:len(sea["seas"])] = sea["seas"]
+        m["sea_land"][i][:len(sea["lands"])] = sea["lands"]
+    for i, c in enumerate(d["canals"]):
+        m["canal_seas"][i], m["canal_lands"][i] = c["seas"], c["lands"]
+    m["capital"] = d["capitals"]
+    axis = np.asarray(d["axis"], dtype=bool)
+    m["is_allied"] = (axis[:, None] == axis[None, :]).astype(np.uint8)
+    return m
+
+
 def start_state():
     """The reference's start position (reference game_data.json:1-42) as 670 bytes (uint8)."""
     s = np.zeros((), dtype=STATE_DTYPE)

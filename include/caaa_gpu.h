@@ -45,6 +45,13 @@ typedef struct CaaaBatchSummary {
 /* replaces initialize_constants() + the engine's global set-up (reference include/engine.h:29,
  * src/engine.cpp:165-178): builds the topology tables on the host and uploads them. */
 int caaa_gpu_init(int device);
+/* The same with the board as data (CaaaMap, caaa_types.h: what the reference compiles in from src/land.cpp, sea.cpp,
+ * canal.cpp, player.cpp).  Dimensions stay 5 lands / 3 seas / 2 canals / 5 players; connectivity, land values, original
+ * owners, capitals, canals and teams are the caller's.  caaa_gpu_init(device) == caaa_gpu_init_map(device, default map).
+ * CAAA_E_ARG for an invalid map, or when the library is already initialised with another one. */
+int caaa_gpu_init_map(int device, const CaaaMap* map);
+int caaa_gpu_default_map(CaaaMap* out);                              /* host only */
+int caaa_gpu_tables_for_map(const CaaaMap* map, CaaaTables* out);    /* host only: initialize_constants() for that board */
 int caaa_gpu_shutdown(void);
 const char* caaa_gpu_last_error(void);
 int caaa_gpu_get_tables(CaaaTables* out);

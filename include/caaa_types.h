@@ -115,6 +115,28 @@ typedef struct CaaaTables {
   uint8_t air_to_land_within[6][8][5];
 } CaaaTables;
 
+/* ---- The board as data: what the reference compiles in from src/land.cpp:4-20, src/sea.cpp:5-8,
+ * src/canal.cpp:3-6 and src/player.cpp:9-13.  Dimensions stay the reference's compile-time macros (5 lands, 3 seas,
+ * 2 canals, 5 players); the connectivity, values, owners, capitals and teams are loadable (caaa_gpu_init_map).
+ * Neighbour lists are directional exactly as in the reference (a land's sea list and a sea's land list are
+ * separate data and need not mirror each other: they do not on the reference's own map). ---- */
+typedef struct CaaaMap {
+  uint8_t land_owner[CAAA_LANDS];        /* Land.original_owner_index */
+  uint8_t land_value[CAAA_LANDS];        /* Land.land_value */
+  uint8_t land_sea_count[CAAA_LANDS];    /* Land.sea_conn_count  (<= 4) */
+  uint8_t land_land_count[CAAA_LANDS];   /* Land.land_conn_count (<= 6) */
+  uint8_t land_sea[CAAA_LANDS][4];       /* Land.connected_sea_index */
+  uint8_t land_land[CAAA_LANDS][6];      /* Land.connected_land_index */
+  uint8_t sea_sea_count[CAAA_SEAS];      /* Sea.sea_conn_count  (<= 7) */
+  uint8_t sea_land_count[CAAA_SEAS];     /* Sea.land_conn_count (<= 6) */
+  uint8_t sea_sea[CAAA_SEAS][7];         /* Sea.connected_sea_index */
+  uint8_t sea_land[CAAA_SEAS][6];        /* Sea.connected_land_index */
+  uint8_t canal_seas[CAAA_CANALS][2];    /* Canal.seas */
+  uint8_t canal_lands[CAAA_CANALS][2];   /* Canal.lands */
+  uint8_t capital[CAAA_PLAYERS];         /* Player.capital_territory_index */
+  uint8_t is_allied[CAAA_PLAYERS][CAAA_PLAYERS]; /* Player.is_allied */
+} CaaaMap;
+
 /* ---- Derived per-game caches (the reference's file-scope globals, src/engine.cpp:120-159),
  * in a fixed wire layout so tests can compare implementations field by field. ---- */
 typedef struct CaaaCacheDump {

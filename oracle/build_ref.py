@@ -134,6 +134,39 @@ typedef struct cJSON cJSON;
 """
 
 
+def write_alt_map_sources(map_json, dst):
+    """The reference's four static-data TUs (src/land.cpp, sea.cpp, canal.cpp, player.cpp) for ANOTHER board of the same
+    dimensions, generated from tests/golden/alt_map.json in the reference's own initialiser format.  The engine, the
+    search and the unit tables are the reference's; only the data differs."""
+    import json
+    with open(map_json) as f:
+        d = json.load(f)
+    pad = lambda xs, n: ", ".join(str(x) for x in (list(xs) + [0] * n)[:n])
+    land = ['#include "land.h"', "#include <array>", "const std::array<Land, LANDS_COUNT> LANDS = {{"]
+    land.append(",\n".join('  {"%s", %d, %d, %d, %d, {%s}, {%s}}' % (l["name"], l["owner"], l["value"], len(l["seas"]), len(l["lands"]),
+                                                                     pad(l["seas"], 4), pad(l["lands"], 6)) for l in d["lands"]))
+    land.append("}};")
+    sea = ['#include "sea.h"', "const Sea SEAS[SEAS_COUNT] = {"]
+    sea.append(",\n".join('  {(char*)"%s", %d, %d, {%s}, {%s}}' % (s["name"], len(s["seas"]), len(s["lands"]), pad(s["seas"], 7), pad(s["lands"], 6))
+                          for s in d["seas"]))
+    sea.append("};")
+    canal = ['#include "canal.h"', "const Canal CANALS[CANALS_COUNT] = {"]
+    canal.append(",\n".join('  {"%s", {%s}, {%s}}' % (c["name"], pad(c["seas"], 2), pad(c["lands"], 2)) for c in d["canals"]))
+    canal.append("};")
+    axis = d["axis"]
+    player = ['#include "player.h"', "const Player PLAYERS[PLAYERS_COUNT] = {"]
+    rows = []
+    for p in range(5):
+        allied = ", ".join("true" if axis[p] == axis[q] else "false" for q in range(5))
+        rows.append('  {"P%d", "P%d", "", %d, %d, {%s}, false}' % (p, p, d["capitals"][p], 1 if axis[p] else 0, allied))
+    player.append(",\n".join(rows))
+    player.append("};")
+    os.makedirs(dst, exist_ok=True)
+    for name, lines in (("land.cpp", land), ("sea.cpp", sea), ("canal.cpp", canal), ("player.cpp", player)):
+        with open(os.path.join(dst, name), "w") as f:
+            f.write("\n".join(lines) + "\n")
+
+
 def main():
     if not os.path.isdir(os.path.join(REF, "src")):
         print(f"build_ref: {REF} not present; keeping any prebuilt oracle/_ref as is", file=sys.stderr)
@@ -174,6 +207,15 @@ def main():
     subprocess.check_call([cxx] + flags + ["-shared", "-o", so] + srcs + ["-lm"])
     cli = os.path.join(OUT, "ref_cli")
     subprocess.check_call([cxx] + flags + ["-o", cli, os.path.join(HERE, "ref_cli.cpp")] + srcs + ["-lm"])
+    # the same engine with the data TUs of a second board (tests/golden/alt_map.json): the oracle of the map-as-data path
+    alt_json = os.path.join(os.path.dirname(HERE), "tests", "golden", "alt_map.json")
+    if os.path.exists(alt_json):
+        alt_src = os.path.join(OUT, "alt_src")
+        shutil.rmtree(alt_src, ignore_errors=True)
+        write_alt_map_sources(alt_json, alt_src)
+        alt = [os.path.join(SRC, tu) for tu in ("engine.cpp", "mcts.cpp", "units.cpp")] + \
+              [os.path.join(alt_src, tu) for tu in ("land.cpp", "sea.cpp", "canal.cpp", "player.cpp")] + [os.path.join(HERE, "ref_shim.cpp")]
+        subprocess.check_call([cxx] + flags + ["-shared", "-o", os.path.join(OUT, "libcaaa_ref_alt.so")] + alt + ["-lm"])
     print(f"build_ref: built {so} and {cli}")
     return 0
 

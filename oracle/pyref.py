@@ -220,6 +220,11 @@ class Ref(_Engine):
         return out
 
 
+class RefAlt(Ref):
+    """The reference engine compiled with the data TUs of the second board (tests/golden/alt_map.json)."""
+    PATH = os.path.join(HERE, "_ref", "libcaaa_ref_alt.so")
+
+
 class Port(_Engine):
     PATH = os.path.join(HERE, "libcaaa_oracle.so")
 

@@ -59,9 +59,17 @@ static void run_until_decision(Game* g) {
 }
 
 extern "C" {
+void caaa_hostsim_set_map(const CaaaMap* m) {  // other boards (same dimensions): rebuilds the tables
+  build_dev_tables(*m, &g_tables);
+  std::memset(&g_game, 0, sizeof(g_game));
+  set_ctx();
+  g_inited = true;
+}
 void caaa_hostsim_init(void) {
   if (g_inited) return;
-  build_dev_tables(&g_tables);
+  CaaaMap m;
+  default_map(&m);
+  build_dev_tables(m, &g_tables);
   std::memset(&g_game, 0, sizeof(g_game));
   set_ctx();
   g_inited = true;
