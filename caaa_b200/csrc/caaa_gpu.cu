@@ -58,7 +58,6 @@ struct RolloutArgs {
   CaaaRolloutStats* stats;    // optional
   CaaaBatchSummary* summary;  // optional
   unsigned long long* ticket;
-  int switch_below;
   int yield_lanes;   // a phase yields once this percentage of its batch is done; stragglers are requeued (0 = never)
   int scan_rounds;   // bitmap words / 32 a claim may look at
   int yield_battles; // like yield_lanes, for the two battle phases only
@@ -609,7 +608,6 @@ static int launch_rollout(const void* d_states, int n_states, unsigned rollouts_
   a.summary = d_summary;
   a.ticket = L.d_ticket;
   {
-    a.switch_below = 0;  // (round 1's queue-length rule; replaced by `patience`)
     const char* yl = std::getenv("CAAA_YIELD");
     a.yield_lanes = yl ? std::atoi(yl) : 0;
     const char* yb = std::getenv("CAAA_YIELD_BATTLES");
