@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--ref-playouts-per-core", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-root-parallel", action="store_true")
-    ap.add_argument("--mcts-iterations", type=int, default=1024, help="leaves per GPU of the root-parallel block (N > 1)")
+    ap.add_argument("--mcts-iterations", type=int, default=2048, help="leaves per GPU of the root-parallel block (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
