@@ -849,7 +849,19 @@ int caaa_gpu_init_map(int device, const CaaaMap* map) {
   CUDA_TRY(cudaFuncSetAttribute(rollout_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, rollout_smem()));
   CUDA_TRY(cudaFuncSetAttribute(prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
-  CUDA_TRY(cudaFuncSetAttribute(battle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BATTLE_SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(battle_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, BattleCfg<32>::SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(battle_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BattleCfg<16>::SMEM));
+  CUDA_TRY(cudaFuncSetAttribute(battle_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BattleCfg<8>::SMEM));
+#define CAAA_POOL_ATTR(NLD, NCB, NLB)                                                                                        \
+  CUDA_TRY(cudaFuncSetAttribute(battle_pool_kernel<NLD, NCB, NLB>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                BattlePoolCfg<NLD, NCB, NLB>::SMEM))
+  CAAA_POOL_ATTR(2, 8, 32);
+  CAAA_POOL_ATTR(1, 8, 32);
+  CAAA_POOL_ATTR(2, 8, 16);
+  CAAA_POOL_ATTR(3, 8, 16);
+  CAAA_POOL_ATTR(2, 6, 32);
+  CAAA_POOL_ATTR(2, 10, 16);
+#undef CAAA_POOL_ATTR
   CUDA_TRY(cudaFuncSetAttribute(actions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
@@ -1060,17 +1072,50 @@ static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t f
   Context& c = g_ctx;
   // every warp takes `run` consecutive states at a time from a device-wide counter: long enough for coalesced refills,
   // short enough that the 148 x 6 warps finish together
-  int run = n / (c.sm_count * BATTLE_WARPS * 8);
+  const char* yd0 = std::getenv("CAAA_BATTLE_YIELD_DIV");
+  const char* bk = std::getenv("CAAA_BATTLE_KERNEL");  // "pool" (regrouped by stage) or "refill" (battle.cuh)
+  if (bk == nullptr || std::strcmp(bk, "refill") != 0) {
+    const char* pc = std::getenv("CAAA_BATTLE_POOL");
+    const int cfg = pc ? std::atoi(pc) : 0;
+    int yield_div = yd0 ? std::atoi(yd0) : 4;
+    if (yield_div < 1) yield_div = 1;
+    int grid = (n + 31) / 32;
+    if (grid > c.sm_count) grid = c.sm_count;
+    CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
+#define CAAA_LAUNCH_POOL(NLD, NCB, NLB)                                                                                     \
+  battle_pool_kernel<NLD, NCB, NLB><<<grid, BattlePoolCfg<NLD, NCB, NLB>::WARPS * 32, BattlePoolCfg<NLD, NCB, NLB>::SMEM, stream>>>( \
+      c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id, (uint8_t*)d_out, d_draws, d_summary, d_counter, yield_div)
+    switch (cfg) {
+      case 1: CAAA_LAUNCH_POOL(1, 8, 32); break;
+      case 2: CAAA_LAUNCH_POOL(2, 8, 16); break;
+      case 3: CAAA_LAUNCH_POOL(3, 8, 16); break;
+      case 4: CAAA_LAUNCH_POOL(2, 6, 32); break;
+      case 5: CAAA_LAUNCH_POOL(2, 10, 16); break;
+      default: CAAA_LAUNCH_POOL(2, 8, 32); break;
+    }
+#undef CAAA_LAUNCH_POOL
+    CUDA_TRY(cudaGetLastError());
+    return CAAA_OK;
+  }
+  const char* bl = std::getenv("CAAA_BATTLE_LANES");  // battle-owning lanes per warp: 32, 16 or 8 (battle.cuh)
+  const int lanes = bl ? std::atoi(bl) : 16;
+  const int warps = lanes == 32 ? BattleCfg<32>::WARPS : lanes == 8 ? BattleCfg<8>::WARPS : BattleCfg<16>::WARPS;
+  int run = n / (c.sm_count * warps * 8);
   run = run < 32 ? 32 : run > 1024 ? 1024 : run / 8 * 8;
   const int want = (n + run - 1) / run;  // warps that can get a run at all
-  int grid = (want + BATTLE_WARPS - 1) / BATTLE_WARPS;
+  int grid = (want + warps - 1) / warps;
   if (grid > c.sm_count) grid = c.sm_count;
   const char* yd = std::getenv("CAAA_BATTLE_YIELD_DIV");  // a phase yields once 1/yield_div of its lanes are done
   int yield_div = yd ? std::atoi(yd) : 4;
   if (yield_div < 1) yield_div = 1;
   CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
-  battle_kernel<<<grid, BATTLE_WARPS * 32, BATTLE_SMEM, stream>>>(c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id,
-                                                                  (uint8_t*)d_out, d_draws, d_summary, d_counter, run, yield_div);
+#define CAAA_LAUNCH_BATTLES(NLANES)                                                                                          \
+  battle_kernel<NLANES><<<grid, BattleCfg<NLANES>::WARPS * 32, BattleCfg<NLANES>::SMEM, stream>>>(                            \
+      c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id, (uint8_t*)d_out, d_draws, d_summary, d_counter, run, yield_div)
+  if (lanes == 32) CAAA_LAUNCH_BATTLES(32);
+  else if (lanes == 8) CAAA_LAUNCH_BATTLES(8);
+  else CAAA_LAUNCH_BATTLES(16);
+#undef CAAA_LAUNCH_BATTLES
   CUDA_TRY(cudaGetLastError());
   return CAAA_OK;
 }
@@ -1115,7 +1160,19 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   const int n_chunks = (int)(((size_t)n + chunk - 1) / chunk);
   const unsigned hw = std::thread::hardware_concurrency();
-  const int copy_threads = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;  // per direction
+  int copy_threads = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;  // per direction
+  if (const char* ct = std::getenv("CAAA_COPY_THREADS")) copy_threads = std::max(1, std::atoi(ct));
+  // buffers the caller has page-locked (cudaHostAlloc / cudaHostRegister) are moved by the copy engines directly,
+  // without the pass through the staging buffers
+  auto page_locked = [](const void* p) {
+    cudaPointerAttributes a;
+    if (p == nullptr || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool in_direct = page_locked(states), out_direct = page_locked(out_states), draws_direct = page_locked(out_draws);
   std::mutex mu;
   std::condition_variable cv;
   int issued = 0, drained = 0;
@@ -1126,8 +1183,9 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
     const int b = k % BattlePipe::NBUF;
     const size_t lo = (size_t)k * chunk, cnt = std::min(chunk, (size_t)n - lo);
     if (cudaEventSynchronize(bp.done[b]) != cudaSuccess) return false;
-    if (out_states) parallel_memcpy((uint8_t*)out_states + lo * CAAA_STATE_BYTES, bp.h_out[b], cnt * CAAA_STATE_BYTES, copy_threads);
-    if (out_draws) std::memcpy(out_draws + lo, bp.h_draws[b], cnt * sizeof(int32_t));
+    if (out_states && !out_direct)
+      parallel_memcpy((uint8_t*)out_states + lo * CAAA_STATE_BYTES, bp.h_out[b], cnt * CAAA_STATE_BYTES, copy_threads);
+    if (out_draws && !draws_direct) std::memcpy(out_draws + lo, bp.h_draws[b], cnt * sizeof(int32_t));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, bp.k0[b], bp.k1[b]) == cudaSuccess) kernel_ms += ms;
     return true;
@@ -1159,16 +1217,24 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
       cv.wait(lk, [&] { return drained > k - BattlePipe::NBUF || failed; });
       if (failed) break;
     }
-    parallel_memcpy(bp.h_in[b], (const uint8_t*)states + lo * CAAA_STATE_BYTES, cnt * CAAA_STATE_BYTES, copy_threads);
+    const uint8_t* h_src = (const uint8_t*)states + lo * CAAA_STATE_BYTES;
+    if (!in_direct) {
+      parallel_memcpy(bp.h_in[b], h_src, cnt * CAAA_STATE_BYTES, copy_threads);
+      h_src = (const uint8_t*)bp.h_in[b];
+    }
     cudaStream_t st = bp.stream[b];
-    cudaError_t e = cudaMemcpyAsync(bp.d_in[b], bp.h_in[b], cnt * CAAA_STATE_BYTES, cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemcpyAsync(bp.d_in[b], h_src, cnt * CAAA_STATE_BYTES, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaEventRecord(bp.k0[b], st);
     if (e == cudaSuccess && launch_battles(bp.d_in[b], (int)cnt, seed, first_game_id + lo, out_states ? bp.d_out[b] : nullptr, bp.d_draws[b],
                                            c.d_summary, c.d_battle_counters + b, st) != CAAA_OK)
       e = cudaErrorLaunchFailure;
     if (e == cudaSuccess) e = cudaEventRecord(bp.k1[b], st);
-    if (e == cudaSuccess && out_states) e = cudaMemcpyAsync(bp.h_out[b], bp.d_out[b], cnt * CAAA_STATE_BYTES, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && out_draws) e = cudaMemcpyAsync(bp.h_draws[b], bp.d_draws[b], cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_states)
+      e = cudaMemcpyAsync(out_direct ? (void*)((uint8_t*)out_states + lo * CAAA_STATE_BYTES) : bp.h_out[b], bp.d_out[b],
+                          cnt * CAAA_STATE_BYTES, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && out_draws)
+      e = cudaMemcpyAsync(draws_direct ? (void*)(out_draws + lo) : (void*)bp.h_draws[b], bp.d_draws[b], cnt * sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaEventRecord(bp.done[b], st);
     if (e != cudaSuccess) rc = fail(CAAA_E_CUDA, "battle pipeline", e);
     if (threaded) {

@@ -158,11 +158,15 @@ class GpuEngine:
                                               out.ctypes.data, caches.ctypes.data, draws.ctypes.data))
         return out, caches, draws
 
-    def resolve_battles(self, states, seed, first_game_id=0):
+    def resolve_battles(self, states, seed, first_game_id=0, out=None, draws=None):
+        """`out` / `draws`: optional caller-owned result arrays (e.g. page-locked ones, which the library then fills by
+        DMA without its staging copy; the same holds for a page-locked `states`)."""
         states = _states(states)
         n = states.shape[0]
-        out = np.empty_like(states)
-        draws = np.zeros(n, dtype=np.int32)
+        out = np.empty_like(states) if out is None else out
+        draws = np.zeros(n, dtype=np.int32) if draws is None else draws
+        assert out.shape == states.shape and out.dtype == np.uint8 and out.flags.c_contiguous
+        assert draws.shape == (n,) and draws.dtype == np.int32 and draws.flags.c_contiguous
         summary = np.zeros(1, dtype=SUMMARY_DTYPE)
         self._check(self.lib.caaa_gpu_resolve_battles(states.ctypes.data, n, int(seed), int(first_game_id),
                                                       out.ctypes.data, draws.ctypes.data, summary.ctypes.data))

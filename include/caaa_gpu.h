@@ -96,7 +96,9 @@ int caaa_gpu_advance(const CaaaGameState* states, int n, uint64_t seed, uint64_t
 
 /* Isolated combat resolution (BASELINE config 3): for each state runs refresh_full_cache,
  * resolve_sea_battles, resolve_land_battles (reference src/engine.cpp:642, 2312, 3055) with random
- * dice and retreat decisions, game id first_game_id + i.  out_states / out_draws may be NULL. */
+ * dice and retreat decisions, game id first_game_id + i.  out_states / out_draws may be NULL.  Pageable buffers go
+ * through the library's page-locked staging buffers (a pipeline of 131 072-state chunks); buffers the caller has
+ * page-locked itself (cudaHostAlloc / cudaHostRegister) are read and written by the copy engines directly. */
 int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, uint64_t first_game_id,
                              CaaaGameState* out_states, int32_t* out_draws, CaaaBatchSummary* summary);
 

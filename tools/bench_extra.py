@@ -37,6 +37,17 @@ def battles(args):
     out, d, summ = eng.resolve_battles(states, 0xBA77, 0)
     wall = time.perf_counter() - t0
     k_ms, draws = float(summ["kernel_ms"]), int(summ["draws"])
+    # the same call with page-locked caller buffers: the copy engines read and write them directly
+    p_in = torch.empty(states.shape, dtype=torch.uint8, pin_memory=True)
+    p_in.numpy()[:] = states
+    p_out = torch.empty(states.shape, dtype=torch.uint8, pin_memory=True)
+    p_draws = torch.empty(states.shape[0], dtype=torch.int32, pin_memory=True)
+    eng.resolve_battles(p_in.numpy()[:1 << 18], 0xBA77, 0, out=p_out.numpy()[:1 << 18], draws=p_draws.numpy()[:1 << 18])
+    t0 = time.perf_counter()
+    _, _, summ_p = eng.resolve_battles(p_in.numpy(), 0xBA77, 0, out=p_out.numpy(), draws=p_draws.numpy())
+    wall_p = time.perf_counter() - t0
+    same_p = bool(np.array_equal(p_out.numpy(), out) and np.array_equal(p_draws.numpy(), d))
+    del p_in, p_out, p_draws
     # kernel alone, inputs resident in HBM (one chunk at a time to bound device memory)
     dev = torch.device("cuda", 0)
     d_in = torch.from_numpy(one).to(dev)
@@ -59,6 +70,8 @@ def battles(args):
                       "hbm_gbs_kernel_resident": n_dev * 1340 / (dev_ms * 1e-3) / 1e9,
                       "hbm_frac_of_6465": n_dev * 1340 / (dev_ms * 1e-3) / 1e9 / 6465.2,
                       "battles_per_sec_kernel_in_pipeline": args.n / (k_ms * 1e-3), "battles_per_sec_e2e": args.n / wall,
+                      "battles_per_sec_e2e_page_locked_buffers": args.n / wall_p, "page_locked_equals_pageable": same_p,
+                      "battles_per_sec_kernel_in_pipeline_page_locked": args.n / (float(summ_p["kernel_ms"]) * 1e-3),
                       "e2e_seconds": wall, "h2d_bytes": int(args.n) * 670, "d2h_bytes": int(args.n) * 674,
                       "mean_draws": draws / args.n}))
 
