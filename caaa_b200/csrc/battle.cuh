@@ -193,10 +193,12 @@ struct BattlePoolCfg {
   static constexpr int WARPS = NLOAD + NCOMBAT;
   static constexpr int STAGE_BYTES = (LB * CAAA_STATE_BYTES + 16 + 15) / 16 * 16;  // LB records + alignment slack
   static constexpr int CTRL_BYTES = (int)((sizeof(BattlePoolCtrl) + 15) / 16 * 16);
-  static constexpr int SLOTS_FIT = (232448 - TABLE_BYTES - NLOAD * STAGE_BYTES - CTRL_BYTES) / (int)sizeof(Game);
+  static constexpr int SLOTS_FIT = (232448 - TABLE_BYTES - NLOAD * STAGE_BYTES - CTRL_BYTES - 16) / (int)sizeof(Game);
   static constexpr int SLOTS = SLOTS_FIT > BP_MAX_WORDS * 32 ? BP_MAX_WORDS * 32 : SLOTS_FIT;
   static constexpr int WORDS = (SLOTS + 31) / 32;  // the last word may be partial
-  static constexpr int SMEM = TABLE_BYTES + SLOTS * (int)sizeof(Game) + NLOAD * STAGE_BYTES + CTRL_BYTES;
+  static constexpr int POOL_BYTES = (SLOTS * (int)sizeof(Game) + 15) / 16 * 16;  // the staging buffers are 16-byte aligned
+  static constexpr int SMEM = TABLE_BYTES + POOL_BYTES + NLOAD * STAGE_BYTES + CTRL_BYTES;
+  static_assert(SMEM <= 232448, "battle pool: shared memory budget");
   static_assert(WORDS >= 1 && LB >= 1 && LB <= 32, "battle pool: configuration");
 };
 
@@ -205,12 +207,12 @@ __global__ void __launch_bounds__((NLOAD + NCOMBAT) * 32, 1) battle_pool_kernel(
                                                                                 unsigned long long seed, unsigned long long first_game_id,
                                                                                 uint8_t* out_states, int32_t* out_draws,
                                                                                 CaaaBatchSummary* summary, unsigned int* work_counter,
-                                                                                int yield_div) {
+                                                                                int yield_div, unsigned long long* dbg) {
   using Cfg = BattlePoolCfg<NLOAD, NCOMBAT, LB>;
   constexpr int WORDS = Cfg::WORDS;
   const DevTables* T = stage_tables(tables);
   Game* const slots = reinterpret_cast<Game*>(smem_raw + TABLE_BYTES);
-  uint8_t* const stage_base = smem_raw + TABLE_BYTES + Cfg::SLOTS * sizeof(Game);
+  uint8_t* const stage_base = smem_raw + TABLE_BYTES + Cfg::POOL_BYTES;
   BattlePoolCtrl* S = reinterpret_cast<BattlePoolCtrl*>(stage_base + NLOAD * Cfg::STAGE_BYTES);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < BNQ * BP_MAX_WORDS) {
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__((NLOAD + NCOMBAT) * 32, 1) battle_pool_kernel(
       any0 |= vbm[q0 * BP_MAX_WORDS + w];
       any1 |= vbm[q1 * BP_MAX_WORDS + w];
     }
+    const long long t_poll = dbg ? clock64() : 0;
     if ((any0 | any1) == 0) {
       if (*vretired >= Cfg::SLOTS || *vaborted) break;
       const int p = *vprogress;  // watchdog: live slots but nothing served by any warp for seconds = a lost slot
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__((NLOAD + NCOMBAT) * 32, 1) battle_pool_kernel(
         break;
       }
       __nanosleep(100);
+      if (dbg && lane == 0) atomicAdd(&dbg[(loader ? 4 : 5) * 4], (unsigned long long)(clock64() - t_poll));  // idle
       continue;
     }
     const int a0 = __popc(any0) + (last_kind == q0 ? 4 : 0), a1 = __popc(any1) + (last_kind == q1 ? 4 : 0);
@@ -362,6 +366,13 @@ __global__ void __launch_bounds__((NLOAD + NCOMBAT) * 32, 1) battle_pool_kernel(
     // ---- route every slot to its next stage: one bit in that stage's bitmap ----
     __threadfence_block();
     if (nxt >= 0) atomicOr(&S->bm[nxt][my_w], 1u << lane);
+    const unsigned requeued = dbg ? __ballot_sync(FULL, nxt == kind) : 0u;
+    if (dbg && lane == 0) {  // CAAA_BATTLE_DEBUG: cycles / slots / claims per stage
+      atomicAdd(&dbg[kind * 4], (unsigned long long)(clock64() - t_poll));
+      atomicAdd(&dbg[kind * 4 + 1], (unsigned long long)nh);
+      atomicAdd(&dbg[kind * 4 + 2], 1ULL);
+      atomicAdd(&dbg[kind * 4 + 3], (unsigned long long)__popc(requeued));  // stragglers back in the same queue
+    }
     const unsigned nret = __popc(__ballot_sync(FULL, retire));
     if (lane == 0 && nret) atomicAdd(&S->retired, (int)nret);
   }

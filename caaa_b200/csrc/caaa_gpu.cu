@@ -855,12 +855,12 @@ int caaa_gpu_init_map(int device, const CaaaMap* map) {
 #define CAAA_POOL_ATTR(NLD, NCB, NLB)                                                                                        \
   CUDA_TRY(cudaFuncSetAttribute(battle_pool_kernel<NLD, NCB, NLB>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                 BattlePoolCfg<NLD, NCB, NLB>::SMEM))
-  CAAA_POOL_ATTR(2, 8, 32);
   CAAA_POOL_ATTR(1, 8, 32);
-  CAAA_POOL_ATTR(2, 8, 16);
-  CAAA_POOL_ATTR(3, 8, 16);
-  CAAA_POOL_ATTR(2, 6, 32);
-  CAAA_POOL_ATTR(2, 10, 16);
+  CAAA_POOL_ATTR(2, 8, 32);
+  CAAA_POOL_ATTR(1, 12, 32);
+  CAAA_POOL_ATTR(1, 16, 32);
+  CAAA_POOL_ATTR(1, 24, 32);
+  CAAA_POOL_ATTR(1, 6, 32);
 #undef CAAA_POOL_ATTR
   CUDA_TRY(cudaFuncSetAttribute(actions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
@@ -1084,17 +1084,33 @@ static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t f
     CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), stream));
 #define CAAA_LAUNCH_POOL(NLD, NCB, NLB)                                                                                     \
   battle_pool_kernel<NLD, NCB, NLB><<<grid, BattlePoolCfg<NLD, NCB, NLB>::WARPS * 32, BattlePoolCfg<NLD, NCB, NLB>::SMEM, stream>>>( \
-      c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id, (uint8_t*)d_out, d_draws, d_summary, d_counter, yield_div)
+      c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id, (uint8_t*)d_out, d_draws, d_summary, d_counter, yield_div, d_dbg)
+    unsigned long long* d_dbg = nullptr;
+    const bool debug = std::getenv("CAAA_BATTLE_DEBUG") != nullptr;  // per-stage cycles / slots / claims on stderr (synchronises)
+    if (debug) {
+      CUDA_TRY(cudaMalloc((void**)&d_dbg, 24 * sizeof(unsigned long long)));
+      CUDA_TRY(cudaMemsetAsync(d_dbg, 0, 24 * sizeof(unsigned long long), stream));
+    }
     switch (cfg) {
-      case 1: CAAA_LAUNCH_POOL(1, 8, 32); break;
-      case 2: CAAA_LAUNCH_POOL(2, 8, 16); break;
-      case 3: CAAA_LAUNCH_POOL(3, 8, 16); break;
-      case 4: CAAA_LAUNCH_POOL(2, 6, 32); break;
-      case 5: CAAA_LAUNCH_POOL(2, 10, 16); break;
-      default: CAAA_LAUNCH_POOL(2, 8, 32); break;
+      case 1: CAAA_LAUNCH_POOL(2, 8, 32); break;
+      case 2: CAAA_LAUNCH_POOL(1, 12, 32); break;
+      case 3: CAAA_LAUNCH_POOL(1, 16, 32); break;
+      case 4: CAAA_LAUNCH_POOL(1, 24, 32); break;
+      case 5: CAAA_LAUNCH_POOL(1, 6, 32); break;
+      default: CAAA_LAUNCH_POOL(1, 8, 32); break;
     }
 #undef CAAA_LAUNCH_POOL
     CUDA_TRY(cudaGetLastError());
+    if (debug) {
+      unsigned long long h[24];
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+      cudaFree(d_dbg);
+      static const char* names[6] = {"load", "sea", "land", "export", "idle(loaders)", "idle(combat)"};
+      for (int k = 0; k < 6; k++)
+        std::fprintf(stderr, "battle pool %-14s cycles %12llu  slots %10llu  claims %9llu  requeued %9llu  slots/claim %.1f\n", names[k],
+                     h[k * 4], h[k * 4 + 1], h[k * 4 + 2], h[k * 4 + 3], h[k * 4 + 2] ? (double)h[k * 4 + 1] / (double)h[k * 4 + 2] : 0.0);
+    }
     return CAAA_OK;
   }
   const char* bl = std::getenv("CAAA_BATTLE_LANES");  // battle-owning lanes per warp: 32, 16 or 8 (battle.cuh)

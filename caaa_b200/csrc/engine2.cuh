@@ -128,8 +128,10 @@ CAAA_HD_NOINLINE void refresh_eot_cache(Game* g, const RunCtx cx) {  // 653-660 
 }
 
 CAAA_HD_NOINLINE void refresh_full_cache(Game* g, const RunCtx cx) {  // 642-652, 661-715
+  // Runs once per imported state (and per battle in the battle kernels): the per-state counts of a location are read
+  // into registers in one go and summed with constant offsets, instead of one dependent byte load per loop trip.
   const int cur = g->cur;
-#pragma unroll 1
+#pragma unroll
   for (int p = 0; p < NP; p++) {
     g->income[p] = 0;
     g->nfact[p] = 0;
@@ -139,38 +141,52 @@ CAAA_HD_NOINLINE void refresh_full_cache(Game* g, const RunCtx cx) {  // 642-652
     const int owner = g->owner[l];
     if (g->factory_max[l] > 0) g->factloc[owner][g->nfact[owner]++] = (uint8_t)l;
     g->income[owner] = (int16_t)(g->income[owner] + CAAA_TAB(cx)->t.land_value[l]);
-#pragma unroll 1
+    uint8_t c[LU_ROW];
+#pragma unroll
+    for (int k = 0; k < LU_ROW; k++) c[k] = g->lu[l][k];
+    uint8_t* mine = utl(g, cur, l);
+#pragma unroll
     for (int u = 0; u < NLT; u++) {
-      const uint8_t* s = lu_ptr(g, l, u);
       uint32_t n = 0;
-#pragma unroll 1
-      for (int k = 0; k < (int)states_land(u); k++) n += s[k];
-      utl(g, cur, l)[u] = (uint8_t)n;
+#pragma unroll
+      for (int k = 0; k < (int)states_land(u); k++) n += c[off_lu(u) + k];
+      mine[u] = (uint8_t)n;
     }
-#pragma unroll 1
+    uint8_t r[NP][NLT];
+#pragma unroll
+    for (int pa = 0; pa < NP; pa++)
+#pragma unroll
+      for (int u = 0; u < NLT; u++) r[pa][u] = utl(g, pa, l)[u];
+#pragma unroll
     for (int pa = 0; pa < NP; pa++) {
-      const uint8_t* r = utl(g, pa, l);
       int n = 0;
-#pragma unroll 1
-      for (int u = 0; u < NLT; u++) n += r[u];
+#pragma unroll
+      for (int u = 0; u < NLT; u++) n += r[pa][u];
       g->tot_land[pa][l] = (int16_t)n;
     }
   }
 #pragma unroll 1
   for (int s = 0; s < NS; s++) {
-#pragma unroll 1
+    uint8_t c[SU_ROW];
+#pragma unroll
+    for (int k = 0; k < SU_ROW; k++) c[k] = g->su[s][k];
+    uint8_t* mine = uts(g, cur, s);
+#pragma unroll
     for (int u = 0; u < NST; u++) {
-      const uint8_t* q = su_ptr(g, s, u);
       uint32_t n = 0;
-#pragma unroll 1
-      for (int k = 0; k < (int)states_sea(u); k++) n += q[k];
-      *cur_sea(g, s, u) = (uint8_t)n;
+#pragma unroll
+      for (int k = 0; k < (int)states_sea(u); k++) n += c[off_sea(u) + k];
+      if (u == BOMBERS_SEA) g->cur_sea_bombers[s] = (uint8_t)n;
+      else mine[u] = (uint8_t)n;
     }
 #pragma unroll 1
     for (int pa = 0; pa < NP; pa++) {
-      const uint8_t* r = uts(g, pa, s);
+      const uint8_t* q = uts(g, pa, s);
+      uint8_t r[NST - 1];
+#pragma unroll
+      for (int u = 0; u < NST - 1; u++) r[u] = q[u];
       int n = 0;
-#pragma unroll 1
+#pragma unroll
       for (int u = 0; u < NST - 1; u++) n += r[u];
       g->tot_sea[pa][s] = (int16_t)n;
     }

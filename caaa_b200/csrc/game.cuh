@@ -188,102 +188,132 @@ CAAA_HD uint32_t dot4(uint32_t a, uint32_t b, uint32_t c) {
 }
 
 // ---- reference layout <-> Game ----
+// N bytes src -> dst with every load issued before the first store: the two pointers may alias as far as the
+// compiler knows, and a byte-by-byte copy would wait a full shared-memory round trip per byte.
+template <int N>
+CAAA_HD void copy_block(uint8_t* dst, const uint8_t* src) {
+  uint8_t t[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) t[k] = src[k];
+#pragma unroll
+  for (int k = 0; k < N; k++) dst[k] = t[k];
+}
+
 // Fills everything that the reference keeps in GameState; derived caches are rebuilt by refresh_full_cache().
 CAAA_HD void import_state(Game* g, const uint8_t* src) {
   const CaaaGameState* st = reinterpret_cast<const CaaaGameState*>(src);
   const int player = st->player_index, cur = player % NP;
   g->player = (uint8_t)player;
   g->cur = (uint8_t)cur;
-#pragma unroll 1
-  for (int p = 0; p < NP; p++) g->money[(cur + p) % NP] = st->money[p];
-#pragma unroll 1
-  for (int a = 0; a < NA; a++) {
-    g->builds_left[a] = st->builds_left[a];
-    g->flagged[a] = st->flagged_for_combat[a];
+  {
+    uint8_t m[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) m[p] = st->money[p];
+    int pa = cur;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      g->money[pa] = m[p];
+      pa = pa + 1 == NP ? 0 : pa + 1;
+    }
   }
-#pragma unroll 1
-  for (int l = 0; l < NL; l++) {
-    const CaaaLandState& ls = st->land_state[l];
-    g->owner[l] = (uint8_t)((ls.owner_idx + cur) % NP);
-    g->factory_hp[l] = ls.factory_hp;
-    g->factory_max[l] = ls.factory_max;
-    g->bombard_max[l] = ls.bombard_max;
-    const uint8_t* u = reinterpret_cast<const uint8_t*>(&ls) + 4;
-#pragma unroll 7
-    for (int k = 0; k < LU_ROW; k++) g->lu[l][k] = u[k];
-  }
-#pragma unroll 1
-  for (int s = 0; s < NS; s++) {
-    const uint8_t* u = reinterpret_cast<const uint8_t*>(&st->units_sea[s]);
-#pragma unroll 19
-    for (int k = 0; k < SU_ROW; k++) g->su[s][k] = u[k];
-  }
-#pragma unroll 1
-  for (int p = 1; p < NP; p++) {
-    const int pa = (cur + p) % NP;
-#pragma unroll 1
+  copy_block<NA>(g->builds_left, st->builds_left);
+  copy_block<NA>(g->flagged, st->flagged_for_combat);
+  {
+    uint8_t h[NL][4];  // owner, factory hp / max, bombard max of the five lands
+#pragma unroll
     for (int l = 0; l < NL; l++)
 #pragma unroll
-      for (int u = 0; u < NLT; u++) utl(g, pa, l)[u] = st->other_land_units[p - 1][l][u];
-#pragma unroll 1
-    for (int s = 0; s < NS; s++)
+      for (int k = 0; k < 4; k++) h[l][k] = reinterpret_cast<const uint8_t*>(&st->land_state[l])[k];
 #pragma unroll
-      for (int u = 0; u < NST - 1; u++) uts(g, pa, s)[u] = st->other_sea_units[p - 1][s][u];
+    for (int l = 0; l < NL; l++) {
+      const int o = h[l][0] + cur;
+      g->owner[l] = (uint8_t)(o >= NP ? o % NP : o);
+      g->factory_hp[l] = (int8_t)h[l][1];
+      g->factory_max[l] = h[l][2];
+      g->bombard_max[l] = h[l][3];
+    }
   }
-  uint32_t sk0 = 0, sk1 = 0;
+#pragma unroll 1
+  for (int l = 0; l < NL; l++) copy_block<LU_ROW>(g->lu[l], reinterpret_cast<const uint8_t*>(&st->land_state[l]) + 4);
+#pragma unroll 1
+  for (int s = 0; s < NS; s++) copy_block<SU_ROW>(g->su[s], reinterpret_cast<const uint8_t*>(&st->units_sea[s]));
+  {
+    int pa = cur;
+#pragma unroll 1
+    for (int p = 1; p < NP; p++) {  // one 30-byte and one 42-byte vector per other player
+      pa = pa + 1 == NP ? 0 : pa + 1;
+      copy_block<NL * NLT>(g->ut[pa], &st->other_land_units[p - 1][0][0]);
+      copy_block<NS*(NST - 1)>(g->ut[pa] + NL * NLT, &st->other_sea_units[p - 1][0][0]);
+    }
+  }
   const uint8_t* sm = &st->skipped_moves[0][0];
-#pragma unroll 8
-  for (int i = 0; i < 32; i++) {
-    sk0 |= (uint32_t)(sm[i] & 1u) << i;
-    sk1 |= (uint32_t)(sm[32 + i] & 1u) << i;
+  uint32_t sk[2];
+#pragma unroll 1
+  for (int w = 0; w < 2; w++) {
+    uint8_t t[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) t[i] = sm[w * 32 + i];
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) v |= (uint32_t)(t[i] & 1u) << i;
+    sk[w] = v;
   }
-  g->skipped[0] = sk0;
-  g->skipped[1] = sk1;
+  g->skipped[0] = sk[0];
+  g->skipped[1] = sk[1];
 }
 
 CAAA_HD void export_state(const Game* g, uint8_t* dst) {
   CaaaGameState* st = reinterpret_cast<CaaaGameState*>(dst);
   const int cur = g->cur;
   st->player_index = g->player;
-#pragma unroll 1
-  for (int p = 0; p < NP; p++) st->money[p] = g->money[(cur + p) % NP];
-#pragma unroll 1
-  for (int a = 0; a < NA; a++) {
-    st->builds_left[a] = g->builds_left[a];
-    st->flagged_for_combat[a] = g->flagged[a];
+  {
+    uint8_t m[NP];
+    int pa = cur;
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      m[p] = g->money[pa];
+      pa = pa + 1 == NP ? 0 : pa + 1;
+    }
+#pragma unroll
+    for (int p = 0; p < NP; p++) st->money[p] = m[p];
   }
-#pragma unroll 1
-  for (int l = 0; l < NL; l++) {
-    CaaaLandState& ls = st->land_state[l];
-    ls.owner_idx = (uint8_t)((g->owner[l] + NP - cur) % NP);
-    ls.factory_hp = g->factory_hp[l];
-    ls.factory_max = g->factory_max[l];
-    ls.bombard_max = g->bombard_max[l];
-    uint8_t* u = reinterpret_cast<uint8_t*>(&ls) + 4;
-#pragma unroll 7
-    for (int k = 0; k < LU_ROW; k++) u[k] = g->lu[l][k];
-  }
-#pragma unroll 1
-  for (int s = 0; s < NS; s++) {
-    uint8_t* u = reinterpret_cast<uint8_t*>(&st->units_sea[s]);
-#pragma unroll 19
-    for (int k = 0; k < SU_ROW; k++) u[k] = g->su[s][k];
-  }
-#pragma unroll 1
-  for (int p = 1; p < NP; p++) {
-    const int pa = (cur + p) % NP;
-#pragma unroll 1
+  copy_block<NA>(st->builds_left, g->builds_left);
+  copy_block<NA>(st->flagged_for_combat, g->flagged);
+  {
+    uint8_t h[NL][4];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const int o = g->owner[l] + NP - cur;
+      h[l][0] = (uint8_t)(o >= NP ? o - NP : o);
+      h[l][1] = (uint8_t)g->factory_hp[l];
+      h[l][2] = g->factory_max[l];
+      h[l][3] = g->bombard_max[l];
+    }
+#pragma unroll
     for (int l = 0; l < NL; l++)
 #pragma unroll
-      for (int u = 0; u < NLT; u++) st->other_land_units[p - 1][l][u] = utl(g, pa, l)[u];
+      for (int k = 0; k < 4; k++) reinterpret_cast<uint8_t*>(&st->land_state[l])[k] = h[l][k];
+  }
 #pragma unroll 1
-    for (int s = 0; s < NS; s++)
-#pragma unroll
-      for (int u = 0; u < NST - 1; u++) st->other_sea_units[p - 1][s][u] = uts(g, pa, s)[u];
+  for (int l = 0; l < NL; l++) copy_block<LU_ROW>(reinterpret_cast<uint8_t*>(&st->land_state[l]) + 4, g->lu[l]);
+#pragma unroll 1
+  for (int s = 0; s < NS; s++) copy_block<SU_ROW>(reinterpret_cast<uint8_t*>(&st->units_sea[s]), g->su[s]);
+  {
+    int pa = cur;
+#pragma unroll 1
+    for (int p = 1; p < NP; p++) {
+      pa = pa + 1 == NP ? 0 : pa + 1;
+      copy_block<NL * NLT>(&st->other_land_units[p - 1][0][0], g->ut[pa]);
+      copy_block<NS*(NST - 1)>(&st->other_sea_units[p - 1][0][0], g->ut[pa] + NL * NLT);
+    }
   }
   uint8_t* sm = &st->skipped_moves[0][0];
-#pragma unroll 8
-  for (int i = 0; i < 64; i++) sm[i] = (uint8_t)((g->skipped[i >> 5] >> (i & 31)) & 1u);
+#pragma unroll 1
+  for (int w = 0; w < 2; w++) {
+    const uint32_t v = g->skipped[w];
+#pragma unroll
+    for (int i = 0; i < 32; i++) sm[w * 32 + i] = (uint8_t)((v >> i) & 1u);
+  }
 }
 
 // the reference's derived globals in the fixed wire layout of CaaaCacheDump (relative player order)
