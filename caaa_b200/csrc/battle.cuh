@@ -2,17 +2,22 @@
 // (reference src/engine.cpp:2312, 3055) on a batch of independent states.
 //
 // Included by caaa_gpu.cu.  One thread per battle -- but a battle lasts anything from one volley to more than a
-// hundred rounds, and a warp that resolves 32 battles side by side runs as long as its longest one: measured, the
-// round-1 kernel and a tile-per-warp rewrite with bulk asynchronous copies both sat at 31 M battles/s with ~2 of
-// 32 lanes busy, whatever the memory path.  So the lanes are REFILLED: a warp owns a contiguous run of states and
-// a cursor into it; the battle phases yield (engine2.cuh keeps a resumable cursor per game) as soon as a quarter
-// of their lanes have finished, the finished lanes export their state, take the next states of the run, and the
-// warp re-enters the phase with the stragglers and the newcomers together.
+// hundred rounds, sea and land battles are different code, and every battle needs its 670-byte record converted to
+// and from the working layout.  Two kernels, in the order they were written:
 //
-// Memory path: states are 670-byte records at the ABI (2-byte aligned).  A refill moves up to 8 consecutive
-// records with warp-wide coalesced 16-bit accesses through a small staging buffer in shared memory; the byte-wise
-// layout conversion (import_state / export_state) and the branchy combat code run out of shared memory.  HBM sees
-// exactly the algorithmic bytes: 670 in + 670 out per battle.
+//  * battle_kernel (the "refill" kernel, CAAA_BATTLE_KERNEL=refill): a warp owns a run of states; its lanes keep a
+//    battle from import to export, the battle phases yield as soon as a quarter of their lanes have finished, the
+//    finished lanes export, take the next states of the run and the warp re-enters the phase with stragglers and
+//    newcomers together.  41-62 M battles/s: lanes in a sea battle, in a land battle and in the layout conversion
+//    never run together, so most instructions issue for 2-8 lanes.
+//  * battle_pool_kernel (shipped): the working sets of an SM live in a CTA-wide pool and are regrouped by what they
+//    are doing -- see the comment above the kernel.  105 M battles/s.
+//
+// Memory path of both: states are 670-byte records at the ABI.  Records enter and leave through small staging
+// buffers in shared memory with warp-wide coalesced accesses (128-bit loads of the aligned window around a run of
+// records; 16-bit stores, a record being only 2-byte aligned); the byte-wise layout conversion (import_state /
+// export_state) and the branchy combat code run out of shared memory.  HBM sees the algorithmic bytes: 670 in + 670
+// out per battle (measured 1.31 KB of DRAM traffic per battle).
 #pragma once
 
 namespace caaa {

@@ -851,16 +851,12 @@ int caaa_gpu_init_map(int device, const CaaaMap* map) {
   CUDA_TRY(cudaFuncSetAttribute(advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(battle_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, BattleCfg<32>::SMEM));
   CUDA_TRY(cudaFuncSetAttribute(battle_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BattleCfg<16>::SMEM));
-  CUDA_TRY(cudaFuncSetAttribute(battle_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BattleCfg<8>::SMEM));
 #define CAAA_POOL_ATTR(NLD, NCB, NLB)                                                                                        \
   CUDA_TRY(cudaFuncSetAttribute(battle_pool_kernel<NLD, NCB, NLB>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                 BattlePoolCfg<NLD, NCB, NLB>::SMEM))
+  CAAA_POOL_ATTR(2, 6, 32);
   CAAA_POOL_ATTR(1, 8, 32);
   CAAA_POOL_ATTR(2, 8, 32);
-  CAAA_POOL_ATTR(1, 12, 32);
-  CAAA_POOL_ATTR(1, 16, 32);
-  CAAA_POOL_ATTR(1, 24, 32);
-  CAAA_POOL_ATTR(1, 6, 32);
 #undef CAAA_POOL_ATTR
   CUDA_TRY(cudaFuncSetAttribute(actions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
   CUDA_TRY(cudaFuncSetAttribute(apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, small_smem()));
@@ -1092,12 +1088,9 @@ static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t f
       CUDA_TRY(cudaMemsetAsync(d_dbg, 0, 24 * sizeof(unsigned long long), stream));
     }
     switch (cfg) {
-      case 1: CAAA_LAUNCH_POOL(2, 8, 32); break;
-      case 2: CAAA_LAUNCH_POOL(1, 12, 32); break;
-      case 3: CAAA_LAUNCH_POOL(1, 16, 32); break;
-      case 4: CAAA_LAUNCH_POOL(1, 24, 32); break;
-      case 5: CAAA_LAUNCH_POOL(1, 6, 32); break;
-      default: CAAA_LAUNCH_POOL(1, 8, 32); break;
+      case 1: CAAA_LAUNCH_POOL(1, 8, 32); break;
+      case 2: CAAA_LAUNCH_POOL(2, 8, 32); break;
+      default: CAAA_LAUNCH_POOL(2, 6, 32); break;  // measured best: 2 loader + 6 combat warps, 199 resident battles per SM
     }
 #undef CAAA_LAUNCH_POOL
     CUDA_TRY(cudaGetLastError());
@@ -1113,9 +1106,9 @@ static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t f
     }
     return CAAA_OK;
   }
-  const char* bl = std::getenv("CAAA_BATTLE_LANES");  // battle-owning lanes per warp: 32, 16 or 8 (battle.cuh)
+  const char* bl = std::getenv("CAAA_BATTLE_LANES");  // refill kernel: battle-owning lanes per warp, 32 or 16 (battle.cuh)
   const int lanes = bl ? std::atoi(bl) : 16;
-  const int warps = lanes == 32 ? BattleCfg<32>::WARPS : lanes == 8 ? BattleCfg<8>::WARPS : BattleCfg<16>::WARPS;
+  const int warps = lanes == 32 ? BattleCfg<32>::WARPS : BattleCfg<16>::WARPS;
   int run = n / (c.sm_count * warps * 8);
   run = run < 32 ? 32 : run > 1024 ? 1024 : run / 8 * 8;
   const int want = (n + run - 1) / run;  // warps that can get a run at all
@@ -1129,7 +1122,6 @@ static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t f
   battle_kernel<NLANES><<<grid, BattleCfg<NLANES>::WARPS * 32, BattleCfg<NLANES>::SMEM, stream>>>(                            \
       c.d_tables, (const uint8_t*)d_states, n, seed, first_game_id, (uint8_t*)d_out, d_draws, d_summary, d_counter, run, yield_div)
   if (lanes == 32) CAAA_LAUNCH_BATTLES(32);
-  else if (lanes == 8) CAAA_LAUNCH_BATTLES(8);
   else CAAA_LAUNCH_BATTLES(16);
 #undef CAAA_LAUNCH_BATTLES
   CUDA_TRY(cudaGetLastError());
@@ -1176,7 +1168,7 @@ int caaa_gpu_resolve_battles(const CaaaGameState* states, int n, uint64_t seed, 
   CUDA_TRY(cudaStreamSynchronize(c.stream));
   const int n_chunks = (int)(((size_t)n + chunk - 1) / chunk);
   const unsigned hw = std::thread::hardware_concurrency();
-  int copy_threads = hw >= 16 ? 4 : hw >= 8 ? 2 : 1;  // per direction
+  int copy_threads = hw >= 16 ? 8 : hw >= 8 ? 4 : hw >= 4 ? 2 : 1;  // per direction
   if (const char* ct = std::getenv("CAAA_COPY_THREADS")) copy_threads = std::max(1, std::atoi(ct));
   // buffers the caller has page-locked (cudaHostAlloc / cudaHostRegister) are moved by the copy engines directly,
   // without the pass through the staging buffers

@@ -1231,43 +1231,59 @@ CAAA_HD_NOINLINE void remove_land_attackers(Game* g, int land, uint32_t hits) { 
     }
   }
 }
+// The casualty loops below have no early exits: a lane whose hits are used up keeps walking the (short) casualty
+// order doing nothing, or leaves through the loop condition.  A `return` from inside the loops would make the function's
+// end the only point where the lanes of a warp meet again, and the lanes would walk the order one after the other.
 CAAA_HD_NOINLINE void remove_sea_defenders(Game* g, const RunCtx cx, int sea, uint32_t hits, bool submerged) {  // 2700-2806
   const int ne = CAAA_TAB(cx)->n_enemies[g->cur], air = sea + NL;
   const uint8_t* en = CAAA_TAB(cx)->enemies_abs[g->cur];
 #pragma unroll 1
   for (int e = 0; e < ne; e++) {  // battleships absorb one hit each
     uint8_t* su = uts(g, en[e], sea);
-    if (su[BATTLESHIPS] == 0) continue;
-    uint32_t taken;
-    const bool done = take_hits(&su[BATTLESHIPS], hits, taken);
-    su[BS_DAMAGED] = (uint8_t)(su[BS_DAMAGED] + taken);
-    if (done) return;
+    const uint32_t have = su[BATTLESHIPS];
+    if (have != 0 && hits != 0) {
+      const uint32_t taken = have < hits ? have : hits;
+      su[BATTLESHIPS] = (uint8_t)(have - taken);
+      su[BS_DAMAGED] = (uint8_t)(su[BS_DAMAGED] + taken);
+      hits -= taken;
+    }
   }
+  uint32_t removed = 0, unblocked = 0;
+  uint64_t order = CAAA_PK(SUBMARINES, DESTROYERS, CARRIERS, CRUISERS, FIGHTERS, BS_DAMAGED, TRANS_EMPTY, TRANS_1I) >> (submerged ? 8 : 0);
 #pragma unroll 1
-  for (int k = submerged ? 1 : 0; k < 13; k++) {
-    const int ut = order_sea_def(k);
+  for (int k = submerged ? 1 : 0; k < 13 && hits != 0; k++) {
+    if (k == 8) order = CAAA_PK(TRANS_1A, TRANS_1T, TRANS_2I, TRANS_1I_1A, TRANS_1I_1T, 0, 0, 0);
+    const int ut = (int)(order & 0xffu);
+    order >>= 8;
     const bool in_blockade_range = k >= DESTROYERS && k <= BS_DAMAGED;  // 2783,2791: order index vs type ids
 #pragma unroll 1
     for (int e = 0; e < ne; e++) {
       const int pa = en[e];
       uint8_t* n = &uts(g, pa, sea)[ut];
-      if (*n == 0) continue;
-      uint32_t taken;
-      const bool done = take_hits(n, hits, taken);
-      g->tot_sea[pa][sea] = (int16_t)(g->tot_sea[pa][sea] - (int)taken);
-      g->enemy_count[air] = (int16_t)(g->enemy_count[air] - (int)taken);
-      if (in_blockade_range) g->blockade[sea] = (uint8_t)(g->blockade[sea] - taken);
-      if (done) return;
+      const uint32_t have = *n;
+      if (have != 0 && hits != 0) {
+        const uint32_t taken = have < hits ? have : hits;
+        *n = (uint8_t)(have - taken);
+        hits -= taken;
+        g->tot_sea[pa][sea] = (int16_t)(g->tot_sea[pa][sea] - (int)taken);
+        removed += taken;
+        if (in_blockade_range) unblocked += taken;
+      }
     }
   }
+  g->enemy_count[air] = (int16_t)(g->enemy_count[air] - (int)removed);
+  g->blockade[sea] = (uint8_t)(g->blockade[sea] - unblocked);
 }
-// attacker casualties among state-0 units of one type; true when all hits are absorbed
-CAAA_HD bool hit_sea_state0(Game* g, int sea, int ut, uint32_t& hits) {
+// attacker casualties among state-0 units of one type
+CAAA_HD void hit_sea_state0(Game* g, int sea, int ut, uint32_t& hits) {
   uint8_t* n = &su_ptr(g, sea, ut)[0];
-  if (*n == 0) return false;
+  const uint32_t have = *n;
+  if (have == 0 || hits == 0) return;
   const int cur = g->cur;
-  uint32_t taken;
-  const bool done = take_hits(n, hits, taken);
+  const bool done = have >= hits;  // all remaining hits absorbed by this type
+  const uint32_t taken = done ? hits : have;
+  *n = (uint8_t)(have - taken);
+  hits -= taken;
   g->tot_sea[cur][sea] = (int16_t)(g->tot_sea[cur][sea] - (int)taken);
   if (ut >= TRANS_EMPTY && ut <= TRANS_1T) {
     g->small_cargo[sea] = (int16_t)(g->small_cargo[sea] - (int)taken);
@@ -1281,47 +1297,47 @@ CAAA_HD bool hit_sea_state0(Game* g, int sea, int ut, uint32_t& hits) {
     *c = 0;
     if (ut == CARRIERS) g->carriers[sea] = 0;
   }
-  return done;
 }
 CAAA_HD_NOINLINE void remove_sea_attackers(Game* g, int sea, uint32_t hits) {  // 2808-2982
   const int cur = g->cur;
   uint8_t* mine = uts(g, cur, sea);
-  uint8_t* bb = &su_ptr(g, sea, BATTLESHIPS)[0];
-  if (*bb > 0) {
-    uint32_t taken;
-    const bool done = take_hits(bb, hits, taken);
-    uint8_t* bd = &su_ptr(g, sea, BS_DAMAGED)[0];
-    *bd = (uint8_t)(*bd + taken);
-    mine[BS_DAMAGED] = (uint8_t)(mine[BS_DAMAGED] + taken);
-    if (done) {
-      mine[BATTLESHIPS] = (uint8_t)(mine[BATTLESHIPS] - taken);
-      return;
+  {
+    uint8_t* bb = &su_ptr(g, sea, BATTLESHIPS)[0];
+    const uint32_t have = *bb;
+    if (have > 0) {
+      const bool done = have >= hits;
+      const uint32_t taken = done ? hits : have;
+      *bb = (uint8_t)(have - taken);
+      hits -= taken;
+      uint8_t* bd = &su_ptr(g, sea, BS_DAMAGED)[0];
+      *bd = (uint8_t)(*bd + taken);
+      mine[BS_DAMAGED] = (uint8_t)(mine[BS_DAMAGED] + taken);
+      mine[BATTLESHIPS] = done ? (uint8_t)(mine[BATTLESHIPS] - taken) : (uint8_t)0;
     }
-    mine[BATTLESHIPS] = 0;
   }
-  if (hit_sea_state0(g, sea, SUBMARINES, hits)) return;
-  if (hit_sea_state0(g, sea, DESTROYERS, hits)) return;
-  if (hit_sea_state0(g, sea, CARRIERS, hits)) return;
-  if (hit_sea_state0(g, sea, CRUISERS, hits)) return;
 #pragma unroll 1
-  for (int k = 0; k < 2; k++) {  // air units in any state, 2915-2942
+  for (int ut = SUBMARINES; ut <= CRUISERS && hits != 0; ut++) hit_sea_state0(g, sea, ut, hits);
+#pragma unroll 1
+  for (int k = 0; k < 2 && hits != 0; k++) {  // air units in any state, 2915-2942
     const int ut = k == 0 ? (int)FIGHTERS : (int)BOMBERS_SEA;
     uint8_t* c = cur_sea(g, sea, ut);
-    if (*c == 0) continue;
+    if (*c != 0) {
+      uint8_t* n = su_ptr(g, sea, ut);
 #pragma unroll 1
-    for (int s = 0; s < 5; s++) {
-      uint8_t* n = &su_ptr(g, sea, ut)[s];
-      if (*n == 0) continue;
-      uint32_t taken;
-      const bool done = take_hits(n, hits, taken);
-      g->tot_sea[cur][sea] = (int16_t)(g->tot_sea[cur][sea] - (int)taken);
-      *c = (uint8_t)(*c - taken);
-      if (done) return;
+      for (int s = 0; s < 5 && hits != 0; s++) {
+        const uint32_t have = n[s];
+        if (have != 0) {
+          const uint32_t taken = have < hits ? have : hits;
+          n[s] = (uint8_t)(have - taken);
+          hits -= taken;
+          g->tot_sea[cur][sea] = (int16_t)(g->tot_sea[cur][sea] - (int)taken);
+          *c = (uint8_t)(*c - taken);
+        }
+      }
     }
   }
 #pragma unroll 1
-  for (int k = 0; k < 8; k++)
-    if (hit_sea_state0(g, sea, order_sea_att3(k), hits)) return;
+  for (int k = 0; k < 8 && hits != 0; k++) hit_sea_state0(g, sea, order_sea_att3(k), hits);
 }
 
 // ---- phase 9: resolve_sea_battles, 2312-2550, 2582-2603 ----
@@ -1358,56 +1374,67 @@ CAAA_HD_NOINLINE int resolve_sea_battles(Game* g, const RunCtx cx, unsigned min,
   }
   bool active = true, stop = false;
   int steps = 0;
+  // One combat round per iteration.  The body has no `continue`: a jump to the loop head from inside a conditional
+  // block would make the loop head the first point where the lanes of a warp meet again, and everything after the
+  // block would run one lane at a time.  `go` carries "this lane is still in this round" instead, and converge()
+  // re-joins the lanes after every block whose length differs from lane to lane.
   for (;;) {
     const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
-    if (!active) continue;
+    if (!active) continue;  // (waits at the vote above; the lanes below are exactly `mact`)
+    bool go = true;
     if (!in_battle) {  // next flagged sea with own units (one sea per iteration keeps the lanes together)
 #pragma unroll 1
       for (; s < NS; s++)
         if (g->flagged[s + NL] != 0 && g->tot_sea[cur][s] != 0) break;
       if (s >= NS) {
         active = false;
-        continue;
-      }
-      const uint8_t* mine0 = uts(g, cur, s);
-      submerged = mine0[DESTROYERS] == 0;
-      bool skip = false;
-      if (g->tot_sea[cur][s] == 2) {  // 2336: literal "== 2"
-        if (submerged) {
-          uint32_t subs = 0;
+        go = false;
+      } else {
+        const uint8_t* mine0 = uts(g, cur, s);
+        submerged = mine0[DESTROYERS] == 0;
+        bool skip = false;
+        if (g->tot_sea[cur][s] == 2) {  // 2336: literal "== 2"
+          if (submerged) {
+            uint32_t subs = 0;
 #pragma unroll 1
-          for (int e = 0; e < ne; e++) subs += uts(g, en[e], s)[SUBMARINES];
-          if ((int)(subs & 0xffu) == g->enemy_count[s]) skip = true;  // 2344: land index
-        }
-        if (!skip)
-#pragma unroll 1
-          for (int ut = CRUISERS; ut <= BS_DAMAGED; ut++) {  // bombardment no longer possible
-            uint8_t* a = su_ptr(g, s, ut);
-            a[0] = (uint8_t)(a[0] + a[1]);
-            a[1] = 0;
+            for (int e = 0; e < ne; e++) subs += uts(g, en[e], s)[SUBMARINES];
+            if ((int)(subs & 0xffu) == g->enemy_count[s]) skip = true;  // 2344: land index
           }
+          if (!skip)
+#pragma unroll 1
+            for (int ut = CRUISERS; ut <= BS_DAMAGED; ut++) {  // bombardment no longer possible
+              uint8_t* a = su_ptr(g, s, ut);
+              a[0] = (uint8_t)(a[0] + a[1]);
+              a[1] = 0;
+            }
+        }
+        if (skip) {
+          s++;
+          go = false;
+        } else {
+          in_battle = true;
+          rounds = 0;
+        }
       }
-      if (skip) {
-        s++;
-        continue;
-      }
-      in_battle = true;
-      rounds = 0;
     }
+    converge<!EXPAND>(mact);
     // ---- one combat round ----
     const int air = s + NL;
-    uint8_t* mine = uts(g, cur, s);
+    uint8_t* mine = uts(g, cur, s < NS ? s : 0);
     bool over = false;
-    if (rounds >= SEA_ROUND_CAP) {  // guard (not in the reference, which would spin for ever)
-      g->status |= CAAA_ERR_SEA_ROUND_CAP;
-      stop = true;
-      active = false;
-      continue;
+    if (go) {
+      if (rounds >= SEA_ROUND_CAP) {  // guard (not in the reference, which would spin for ever)
+        g->status |= CAAA_ERR_SEA_ROUND_CAP;
+        stop = true;
+        active = false;
+        go = false;
+      } else {
+        rounds++;
+      }
     }
-    rounds++;
-    if (g->flagged[air] == 1) {  // retreat option, 2368-2406
+    if (go && g->flagged[air] == 1) {  // retreat option, 2368-2406
       uint32_t n = 0;
       if (g->cur_sea_bombers[s] + mine[FIGHTERS] + mine[SUBMARINES] + mine[DESTROYERS] + mine[CARRIERS] + mine[CRUISERS] +
                   mine[BATTLESHIPS] + mine[BS_DAMAGED] > 0 ||
@@ -1423,20 +1450,24 @@ CAAA_HD_NOINLINE int resolve_sea_battles(Game* g, const RunCtx cx, unsigned min,
         uint32_t da = g->vm[0];
         if (n > 1) {
           if (g->answers_remaining == 0) {
-        stop = true;
-        active = false;
-        continue;
-      }
-          da = ai_input<EXPAND>(g, cx);
+            stop = true;
+            active = false;
+            go = false;
+          } else {
+            da = ai_input<EXPAND>(g, cx);
+          }
         }
-        const int ds = (uint8_t)(da - NL);
-        if (ds < NS && t.sea_dist[g->canal_state][s][ds] == 1 && g->flagged[da] == 0) {
-          sea_retreat(g, s, ds);
-          over = true;
+        if (go) {
+          const int ds = (uint8_t)(da - NL);
+          if (ds < NS && t.sea_dist[g->canal_state][s][ds] == 1 && g->flagged[da] == 0) {
+            sea_retreat(g, s, ds);
+            over = true;
+          }
         }
       }
     }
-    if (!over) {
+    converge<!EXPAND>(mact);
+    if (go && !over) {
       g->flagged[air] = 1;
       bool targets = false;
       if (mine[DESTROYERS]) {
@@ -1473,18 +1504,24 @@ CAAA_HD_NOINLINE int resolve_sea_battles(Game* g, const RunCtx cx, unsigned min,
         over = true;
       }
     }
-    if (!over) {
+    const bool fight = go && !over;
+    const unsigned mfight = vote_ballot<!EXPAND>(mact, fight);  // (also re-joins the lanes)
+    if (fight) {
       // sub volley: only state-0 attacking subs count (2484)
       int admg = su_ptr(g, s, SUBMARINES)[0] * 2;
       uint32_t ahits = attacker_hits(g, cx, admg);
+      uint32_t dhits = 0;
       if (!submerged) {
         int ddmg = 0;
 #pragma unroll 1
         for (int e = 0; e < ne; e++) ddmg += uts(g, en[e], s)[SUBMARINES];
-        const uint32_t dhits = defender_hits(g, cx, ddmg);
-        if (dhits > 0) remove_sea_attackers(g, s, dhits);
+        dhits = defender_hits(g, cx, ddmg);
       }
+      converge<!EXPAND>(mfight);
+      if (dhits > 0) remove_sea_attackers(g, s, dhits);
+      converge<!EXPAND>(mfight);
       if (ahits > 0) remove_sea_defenders(g, cx, s, ahits, submerged);
+      converge<!EXPAND>(mfight);
       // main volley, 2513-2542
       admg = mine[DESTROYERS] * 2 + mine[CARRIERS] * 1 + mine[CRUISERS] * 3 + mine[BATTLESHIPS] * 4 + mine[BS_DAMAGED] * 4 +
              mine[FIGHTERS] * 3 + g->cur_sea_bombers[s] * 4;
@@ -1493,15 +1530,18 @@ CAAA_HD_NOINLINE int resolve_sea_battles(Game* g, const RunCtx cx, unsigned min,
 #pragma unroll 1
       for (int e = 0; e < ne; e++)  // 2527-2530: type ids 0..4 (only fighters have a defence value) + fighters again
         ddmg += uts(g, en[e], s)[FIGHTERS] * 4 * 2;
-      const uint32_t dhits = defender_hits(g, cx, ddmg);
+      dhits = defender_hits(g, cx, ddmg);
+      converge<!EXPAND>(mfight);
       if (dhits > 0) remove_sea_attackers(g, s, dhits);
+      converge<!EXPAND>(mfight);
       if (ahits > 0) remove_sea_defenders(g, cx, s, ahits, submerged);
+      converge<!EXPAND>(mfight);
       if (g->enemy_count[air] == 0 || g->tot_sea[cur][s] == 0) {
         g->flagged[air] = 0;
         over = true;
       }
     }
-    if (over) {
+    if (go && over) {
       in_battle = false;
       s++;
     }

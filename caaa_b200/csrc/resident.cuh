@@ -1,4 +1,6 @@
-// resident.cuh -- SM-resident, phase-regrouped rollout kernel (the shipped one).
+// resident.cuh -- SM-resident, phase-regrouped rollout kernel (an experiment kept as CAAA_ROLLOUT_KERNEL=resident: measured
+// 0.52-0.65 M playouts/s against 1.67 M for the pool kernel in stream.cuh, because every warp of an SM ends up in another phase;
+// the same design is what the battle pool kernel in battle.cuh uses, where an SM only has four stages).
 //
 // Included by caaa_gpu.cu (after RolloutArgs / LaneTotals / finish_playout).
 //

@@ -10,7 +10,7 @@ st = torch.cuda.current_stream().cuda_stream
 eng.resolve_battles_device(d_in.data_ptr(), N, 0xBA77, 0, d_out.data_ptr(), d_draws.data_ptr(), None, st)
 torch.cuda.synchronize()
 os.environ['CAAA_BATTLE_DEBUG'] = '1'
-for cfg, div in ((0, 4), (1, 4), (1, 2), (1, 32)):
+for cfg, div in ((0, 4), (1, 4)):
     os.environ['CAAA_BATTLE_POOL'] = str(cfg); os.environ['CAAA_BATTLE_YIELD_DIV'] = str(div)
     print(f"--- pool config {cfg} yield_div {div}", file=sys.stderr, flush=True)
     eng.resolve_battles_device(d_in.data_ptr(), N, 0xBA77, 0, d_out.data_ptr(), d_draws.data_ptr(), None, st)

@@ -10,8 +10,8 @@ N = 1 << 20
 d_in = torch.from_numpy(synth.battle_states(N, seed=0xBA77)).cuda()
 d_out = torch.empty_like(d_in); d_draws = torch.empty(N, dtype=torch.int32, device='cuda')
 st = torch.cuda.current_stream().cuda_stream
-for lanes in (32, 16):
-    os.environ['CAAA_BATTLE_LANES'] = str(lanes)
+for lanes in (16,):
+    os.environ['CAAA_BATTLE_LANES'] = str(lanes); os.environ.setdefault('CAAA_BATTLE_POOL', '0')
     for label, outp in (("export", d_out.data_ptr()), ("no export", None)):
         for _ in range(2):
             eng.resolve_battles_device(d_in.data_ptr(), N, 0xBA77, 0, outp, d_draws.data_ptr(), None, st)

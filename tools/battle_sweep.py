@@ -9,7 +9,7 @@ one = synth.battle_states(N, seed=0xBA77)
 d_in = torch.from_numpy(one).cuda(); d_out = torch.empty_like(d_in); d_draws = torch.empty(N, dtype=torch.int32, device='cuda')
 st = torch.cuda.current_stream().cuda_stream
 ref = None
-variants = [("refill", {"CAAA_BATTLE_LANES": "16"})] + [("pool", {"CAAA_BATTLE_POOL": str(c)}) for c in range(6)]
+variants = [("refill", {"CAAA_BATTLE_LANES": "16"})] + [("pool", {"CAAA_BATTLE_POOL": str(c)}) for c in range(3)]
 divs = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["4"])]
 for kern, env in variants:
     os.environ['CAAA_BATTLE_KERNEL'] = kern
