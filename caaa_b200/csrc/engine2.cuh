@@ -1181,59 +1181,66 @@ CAAA_HD bool take_hits(uint8_t* n, uint32_t& hits, uint32_t& taken) {
   taken = hits;
   return true;
 }
+// The casualty loops have no early exits: a lane whose hits are used up leaves through the loop condition.  A `return`
+// from inside the loops would make the function's end the only point where the lanes of a warp meet again, and the
+// lanes would walk the casualty order one after the other.
 CAAA_HD_NOINLINE void remove_land_defenders(Game* g, const RunCtx cx, int land, uint32_t hits) {  // 2613-2641
   const int ne = CAAA_TAB(cx)->n_enemies[g->cur];
   const uint8_t* en = CAAA_TAB(cx)->enemies_abs[g->cur];
+  uint32_t removed = 0;
 #pragma unroll 1
-  for (int k = 0; k < 6; k++) {
+  for (int k = 0; k < 6 && hits != 0; k++) {
     const int ut = order_land_def(k);
 #pragma unroll 1
     for (int e = 0; e < ne; e++) {
       const int pa = en[e];
       uint8_t* n = &utl(g, pa, land)[ut];
-      if (*n == 0) continue;
-      uint32_t taken;
-      const bool done = take_hits(n, hits, taken);
-      g->tot_land[pa][land] = (int16_t)(g->tot_land[pa][land] - (int)taken);
-      g->enemy_count[land] = (int16_t)(g->enemy_count[land] - (int)taken);
-      if (done) return;
+      const uint32_t have = *n;
+      if (have != 0 && hits != 0) {
+        const uint32_t taken = have < hits ? have : hits;
+        *n = (uint8_t)(have - taken);
+        hits -= taken;
+        g->tot_land[pa][land] = (int16_t)(g->tot_land[pa][land] - (int)taken);
+        removed += taken;
+      }
     }
   }
+  g->enemy_count[land] = (int16_t)(g->enemy_count[land] - (int)removed);
 }
 CAAA_HD_NOINLINE void remove_land_attackers(Game* g, int land, uint32_t hits) {  // 2642-2698
   const int cur = g->cur;
   uint8_t* mine = utl(g, cur, land);
 #pragma unroll 1
-  for (int ut = INFANTRY; ut <= TANKS; ut++) {  // ORDER_OF_LAND_ATTACKERS_1, state 0 only
+  for (int ut = INFANTRY; ut <= TANKS && hits != 0; ut++) {  // ORDER_OF_LAND_ATTACKERS_1, state 0 only
     uint8_t* n = &lu_ptr(g, land, ut)[0];
-    if (*n == 0) continue;
-    uint32_t taken;
-    const bool done = take_hits(n, hits, taken);
-    g->tot_land[cur][land] = (int16_t)(g->tot_land[cur][land] - (int)taken);
-    if (done) {
-      mine[ut] = (uint8_t)(mine[ut] - taken);
-      return;
+    const uint32_t have = *n;
+    if (have != 0) {
+      const bool done = have >= hits;  // all remaining hits absorbed by this type
+      const uint32_t taken = done ? hits : have;
+      *n = (uint8_t)(have - taken);
+      hits -= taken;
+      g->tot_land[cur][land] = (int16_t)(g->tot_land[cur][land] - (int)taken);
+      mine[ut] = done ? (uint8_t)(mine[ut] - taken) : (uint8_t)0;
     }
-    mine[ut] = 0;
   }
 #pragma unroll 1
-  for (int ut = FIGHTERS; ut <= BOMBERS_LAND_AIR; ut++) {  // ORDER_OF_LAND_ATTACKERS_2, states 1..n-2
-    if (mine[ut] == 0) continue;
+  for (int ut = FIGHTERS; ut <= BOMBERS_LAND_AIR && hits != 0; ut++) {  // ORDER_OF_LAND_ATTACKERS_2, states 1..n-2
+    if (mine[ut] != 0) {
+      uint8_t* n = lu_ptr(g, land, ut);
 #pragma unroll 1
-    for (int s = 1; s < (int)states_land(ut) - 1; s++) {
-      uint8_t* n = &lu_ptr(g, land, ut)[s];
-      if (*n == 0) continue;
-      uint32_t taken;
-      const bool done = take_hits(n, hits, taken);
-      mine[ut] = (uint8_t)(mine[ut] - taken);
-      g->tot_land[cur][land] = (int16_t)(g->tot_land[cur][land] - (int)taken);
-      if (done) return;
+      for (int s = 1; s < (int)states_land(ut) - 1 && hits != 0; s++) {
+        const uint32_t have = n[s];
+        if (have != 0) {
+          const uint32_t taken = have < hits ? have : hits;
+          n[s] = (uint8_t)(have - taken);
+          hits -= taken;
+          mine[ut] = (uint8_t)(mine[ut] - taken);
+          g->tot_land[cur][land] = (int16_t)(g->tot_land[cur][land] - (int)taken);
+        }
+      }
     }
   }
 }
-// The casualty loops below have no early exits: a lane whose hits are used up keeps walking the (short) casualty
-// order doing nothing, or leaves through the loop condition.  A `return` from inside the loops would make the function's
-// end the only point where the lanes of a warp meet again, and the lanes would walk the order one after the other.
 CAAA_HD_NOINLINE void remove_sea_defenders(Game* g, const RunCtx cx, int sea, uint32_t hits, bool submerged) {  // 2700-2806
   const int ne = CAAA_TAB(cx)->n_enemies[g->cur], air = sea + NL;
   const uint8_t* en = CAAA_TAB(cx)->enemies_abs[g->cur];
@@ -1681,82 +1688,90 @@ CAAA_HD_NOINLINE int resolve_land_battles(Game* g, const RunCtx cx, unsigned min
     const unsigned mact = vote_ballot<!EXPAND>(m, active);  // the lanes that take part in this iteration
     if (mact == 0) break;
     if (should_yield<!EXPAND>(m, active, yield, steps)) break;
-    if (!active) continue;
+    if (!active) continue;  // (waits at the vote above; the lanes below are exactly `mact`)
+    // no `continue` below, converge() after the variable-length blocks: see resolve_sea_battles
+    bool go = true;
     if (!in_battle) {
 #pragma unroll 1
       for (; l < NL; l++)
         if (g->flagged[l] != 0 && g->tot_land[cur][l] != 0) break;
       if (l >= NL) {
         active = false;
-        continue;
-      }
-      uint8_t* mine = utl(g, cur, l);
-      int16_t* my_total = &g->tot_land[cur][l];
-      bool skip = false;
-      if (g->flagged[l] == 2) {
-        if (mine[BOMBERS_LAND_AIR] > 0 && *my_total == mine[BOMBERS_LAND_AIR]) {  // strategic bombing 3088-3125
-          uint32_t ahits = 0;  // uninitialised in the reference when the factory is already at -max; same result
-          if (g->factory_hp[l] > -(int)g->factory_max[l]) {
-            uint32_t dh = defender_hits(g, cx, mine[BOMBERS_LAND_AIR]);
-            if (dh > 0) hit_air_states(g, l, BOMBERS_LAND_AIR, 1, 6, dh, false);
-            ahits = attacker_hits(g, cx, mine[BOMBERS_LAND_AIR] * 21);
-          }
-          const int hp = g->factory_hp[l] - (int)ahits, floor_hp = -(int)g->factory_max[l];
-          g->factory_hp[l] = (int8_t)(hp > floor_hp ? hp : floor_hp);
-          skip = true;
-        } else {
-          if (g->bombard_max[l] > 0) {  // shore bombardment 3134-3158
-            int admg = 0;
+        go = false;
+      } else {
+        uint8_t* mine = utl(g, cur, l);
+        int16_t* my_total = &g->tot_land[cur][l];
+        bool skip = false;
+        if (g->flagged[l] == 2) {
+          if (mine[BOMBERS_LAND_AIR] > 0 && *my_total == mine[BOMBERS_LAND_AIR]) {  // strategic bombing 3088-3125
+            uint32_t ahits = 0;  // uninitialised in the reference when the factory is already at -max; same result
+            if (g->factory_hp[l] > -(int)g->factory_max[l]) {
+              uint32_t dh = defender_hits(g, cx, mine[BOMBERS_LAND_AIR]);
+              if (dh > 0) hit_air_states(g, l, BOMBERS_LAND_AIR, 1, 6, dh, false);
+              ahits = attacker_hits(g, cx, mine[BOMBERS_LAND_AIR] * 21);
+            }
+            const int hp = g->factory_hp[l] - (int)ahits, floor_hp = -(int)g->factory_max[l];
+            g->factory_hp[l] = (int8_t)(hp > floor_hp ? hp : floor_hp);
+            skip = true;
+          } else {
+            if (g->bombard_max[l] > 0) {  // shore bombardment 3134-3158
+              int admg = 0;
 #pragma unroll 1
-            for (int ut = BS_DAMAGED; ut >= CRUISERS; ut--)
+              for (int ut = BS_DAMAGED; ut >= CRUISERS; ut--)
 #pragma unroll 1
-              for (int i = 0; i < t.l2s_count[l]; i++) {
-                uint8_t* ships = su_ptr(g, t.l2s_conn[l][i], ut);
+                for (int i = 0; i < t.l2s_count[l]; i++) {
+                  uint8_t* ships = su_ptr(g, t.l2s_conn[l][i], ut);
 #pragma unroll 1
-                while (ships[1] > 0 && g->bombard_max[l] > 0) {
-                  admg += attack_sea(ut);
-                  ships[0]++;
-                  ships[1]--;
-                  g->bombard_max[l]--;
+                  while (ships[1] > 0 && g->bombard_max[l] > 0) {
+                    admg += attack_sea(ut);
+                    ships[0]++;
+                    ships[1]--;
+                    g->bombard_max[l]--;
+                  }
                 }
-              }
-            g->bombard_max[l] = 0;
-            const uint32_t ahits = attacker_hits(g, cx, admg);
-            if (ahits > 0) remove_land_defenders(g, cx, l, ahits);
-          }
-          const uint32_t air_units = (uint8_t)(mine[FIGHTERS] + mine[BOMBERS_LAND_AIR]);  // AA fire 3160-3216
-          if (air_units > 0) {
-            int aa = 0;
+              g->bombard_max[l] = 0;
+              const uint32_t ahits = attacker_hits(g, cx, admg);
+              if (ahits > 0) remove_land_defenders(g, cx, l, ahits);
+            }
+            const uint32_t air_units = (uint8_t)(mine[FIGHTERS] + mine[BOMBERS_LAND_AIR]);  // AA fire 3160-3216
+            if (air_units > 0) {
+              int aa = 0;
 #pragma unroll 1
-            for (int e = 0; e < ne; e++) aa += utl(g, en[e], l)[AA_GUNS];
-            if (aa > 0) {
-              uint32_t dh = defender_hits(g, cx, (uint8_t)(air_units * 3));
-              if (dh > 0) hit_air_states(g, l, FIGHTERS, 0, 5, dh, true);
-              if (dh > 0) hit_air_states(g, l, BOMBERS_LAND_AIR, 0, 7, dh, true);
+              for (int e = 0; e < ne; e++) aa += utl(g, en[e], l)[AA_GUNS];
+              if (aa > 0) {
+                uint32_t dh = defender_hits(g, cx, (uint8_t)(air_units * 3));
+                if (dh > 0) hit_air_states(g, l, FIGHTERS, 0, 5, dh, true);
+                if (dh > 0) hit_air_states(g, l, BOMBERS_LAND_AIR, 0, 7, dh, true);
+              }
+            }
+            if (*my_total == 0) {
+              skip = true;
+            } else if (g->enemy_count[l] == 0) {
+              if (mine[INFANTRY] + mine[ARTILLERY] + mine[TANKS] > 0) conquer_land(g, cx, l);
+              skip = true;
             }
           }
-          if (*my_total == 0) {
-            skip = true;
-          } else if (g->enemy_count[l] == 0) {
-            if (mine[INFANTRY] + mine[ARTILLERY] + mine[TANKS] > 0) conquer_land(g, cx, l);
-            skip = true;
-          }
+        }
+        if (skip) {
+          l++;
+          go = false;
+        } else {
+          in_battle = true;
+          rounds = 0;
         }
       }
-      if (skip) {
-        l++;
-        continue;
-      }
-      in_battle = true;
-      rounds = 0;
     }
+    converge<!EXPAND>(mact);
     // ---- one combat round ----
-    uint8_t* mine = utl(g, cur, l);
-    int16_t* my_total = &g->tot_land[cur][l];
+    const int lc = l < NL ? l : 0;  // (a lane that is not `go` may stand past the last land)
+    uint8_t* mine = utl(g, cur, lc);
+    int16_t* my_total = &g->tot_land[cur][lc];
     bool over = false;
-    rounds = (rounds + 1) & 0xffu;  // uint8 counter in the reference
-    if (*my_total == 0) over = true;
-    if (!over && g->flagged[l] == 1) {  // retreat option 3256-3299
+    if (go) {
+      rounds = (rounds + 1) & 0xffu;  // uint8 counter in the reference
+      if (*my_total == 0) over = true;
+    }
+    if (go && !over && g->flagged[l] == 1) {  // retreat option 3256-3299
       g->vm[0] = (uint8_t)l;
       uint32_t n = 1;
 #pragma unroll 1
@@ -1768,13 +1783,14 @@ CAAA_HD_NOINLINE int resolve_land_battles(Game* g, const RunCtx cx, unsigned min
       uint32_t dst = g->vm[0];
       if (n > 1) {
         if (g->answers_remaining == 0) {
-        stop = true;
-        active = false;
-        continue;
+          stop = true;
+          active = false;
+          go = false;
+        } else {
+          dst = ai_input<EXPAND>(g, cx);
+        }
       }
-        dst = ai_input<EXPAND>(g, cx);
-      }
-      if ((uint32_t)l != dst || rounds > 100) {
+      if (go && ((uint32_t)l != dst || rounds > 100)) {
         const int dl = dst < (uint32_t)NL ? (int)dst : l;  // dst is always a land here
 #pragma unroll 1
         for (int ut = INFANTRY; ut <= TANKS; ut++) {
@@ -1790,7 +1806,9 @@ CAAA_HD_NOINLINE int resolve_land_battles(Game* g, const RunCtx cx, unsigned min
         over = true;
       }
     }
-    if (!over) {
+    const bool fight = go && !over;
+    const unsigned mfight = vote_ballot<!EXPAND>(mact, fight);  // (also re-joins the lanes)
+    if (fight) {
       g->flagged[l] = 1;
       const int inf = mine[INFANTRY], art = mine[ARTILLERY];
       const int admg = mine[FIGHTERS] * 3 + mine[BOMBERS_LAND_AIR] * 4 + inf + art * 2 + mine[TANKS] * 3 + (inf < art ? inf : art);
@@ -1803,8 +1821,11 @@ CAAA_HD_NOINLINE int resolve_land_battles(Game* g, const RunCtx cx, unsigned min
         ddmg += eu[INFANTRY] * 2 + eu[ARTILLERY] * 2 + eu[TANKS] * 3 + eu[FIGHTERS] * 4 + eu[BOMBERS_LAND_AIR];
         dh = defender_hits(g, cx, ddmg);
       }
+      converge<!EXPAND>(mfight);
       if (dh > 0) remove_land_attackers(g, l, dh);
+      converge<!EXPAND>(mfight);
       if (ahits > 0) remove_land_defenders(g, cx, l, ahits);
+      converge<!EXPAND>(mfight);
       if (*my_total == 0) {
         over = true;
       } else if (g->enemy_count[l] == 0) {
@@ -1812,7 +1833,7 @@ CAAA_HD_NOINLINE int resolve_land_battles(Game* g, const RunCtx cx, unsigned min
         over = true;
       }
     }
-    if (over) {
+    if (go && over) {
       in_battle = false;
       l++;
     }
