@@ -132,6 +132,37 @@ def test_battle_sweep_properties(eng):
             before["land_state"]["infantry"].astype(np.int32).sum(axis=(-1, -2))).all()
 
 
+def test_battle_kernels_and_buffers_agree(eng):
+    """The shipped pool kernel in its three warp splits and the refill kernel (16 / 32 battle-owning lanes) resolve a
+    ragged multi-chunk batch identically, and page-locked caller buffers (moved by the copy engines directly, no staging
+    copy) give what pageable ones give."""
+    import torch
+    n = 2 * 131072 + 4321  # three pipeline chunks, the last one ragged
+    bs = np.tile(synth.battle_states(1 << 14, seed=77), (n // (1 << 14) + 1, 1))[:n]
+    want, want_draws, summ = eng.resolve_battles(bs, 555, 9_000_000_000)
+    assert summ["playouts"] == n
+    saved = {k: os.environ.get(k) for k in ("CAAA_BATTLE_KERNEL", "CAAA_BATTLE_POOL", "CAAA_BATTLE_LANES")}
+    try:
+        for env in ({"CAAA_BATTLE_POOL": "1"}, {"CAAA_BATTLE_POOL": "2"}, {"CAAA_BATTLE_KERNEL": "refill", "CAAA_BATTLE_LANES": "16"},
+                    {"CAAA_BATTLE_KERNEL": "refill", "CAAA_BATTLE_LANES": "32"}):
+            for k in saved:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            out, draws, _ = eng.resolve_battles(bs[:70_001], 555, 9_000_000_000)
+            assert np.array_equal(out, want[:70_001]) and np.array_equal(draws, want_draws[:70_001]), env
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    p_in = torch.empty(bs.shape, dtype=torch.uint8, pin_memory=True)
+    p_in.numpy()[:] = bs
+    p_out = torch.zeros(bs.shape, dtype=torch.uint8, pin_memory=True)
+    p_draws = torch.zeros(n, dtype=torch.int32, pin_memory=True)
+    eng.resolve_battles(p_in.numpy(), 555, 9_000_000_000, out=p_out.numpy(), draws=p_draws.numpy())
+    assert np.array_equal(p_out.numpy(), want) and np.array_equal(p_draws.numpy(), want_draws)
+
+
 def test_expansion_golden(eng):
     g = np.load(os.path.join(GOLD, "expansion.npz"))
     n_actions, actions, children, status = eng.expand(g["leaves"])
