@@ -11,7 +11,7 @@
 //    newcomers together.  41-62 M battles/s: lanes in a sea battle, in a land battle and in the layout conversion
 //    never run together, so most instructions issue for 2-8 lanes.
 //  * battle_pool_kernel (shipped): the working sets of an SM live in a CTA-wide pool and are regrouped by what they
-//    are doing -- see the comment above the kernel.  105 M battles/s.
+//    are doing -- see the comment above the kernel.  111 M battles/s.
 //
 // Memory path of both: states are 670-byte records at the ABI.  Records enter and leave through small staging
 // buffers in shared memory with warp-wide coalesced accesses (128-bit loads of the aligned window around a run of
