@@ -1066,8 +1066,7 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes, int thread
 static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t first_game_id, void* d_out, int32_t* d_draws,
                           CaaaBatchSummary* d_summary, unsigned int* d_counter, cudaStream_t stream) {
   Context& c = g_ctx;
-  // every warp takes `run` consecutive states at a time from a device-wide counter: long enough for coalesced refills,
-  // short enough that the 148 x 6 warps finish together
+  // pool kernel (default): one persistent CTA per SM; loader warps take the next <= 32 states from a device-wide counter
   const char* yd0 = std::getenv("CAAA_BATTLE_YIELD_DIV");
   const char* bk = std::getenv("CAAA_BATTLE_KERNEL");  // "pool" (regrouped by stage) or "refill" (battle.cuh)
   if (bk == nullptr || std::strcmp(bk, "refill") != 0) {
@@ -1106,6 +1105,8 @@ static int launch_battles(const void* d_states, int n, uint64_t seed, uint64_t f
     }
     return CAAA_OK;
   }
+  // refill kernel: every warp takes `run` consecutive states at a time from the device-wide counter: long enough for
+  // coalesced refills, short enough that the warps of all SMs finish together
   const char* bl = std::getenv("CAAA_BATTLE_LANES");  // refill kernel: battle-owning lanes per warp, 32 or 16 (battle.cuh)
   const int lanes = bl ? std::atoi(bl) : 16;
   const int warps = lanes == 32 ? BattleCfg<32>::WARPS : BattleCfg<16>::WARPS;
