@@ -117,3 +117,20 @@ def test_merged_land_phases_bit_exact(port, hostsim):
         assert np.array_equal(want, hostsim.rollout_many_merged(s, 0, 400, budget)), budget
     for i, st in enumerate(snapshots(port, 12)[::3]):
         assert np.array_equal(port.rollout_many(st, 7000 + 10 * i, 2), hostsim.rollout_many_merged(st, 7000 + 10 * i, 2, 2)), i
+
+
+def test_isolated_battles_bit_exact(port, hostsim):
+    """The combat rounds and casualty loops (written without early exits so that the lanes of a warp reconverge) against
+    the oracle on randomised battle states, from sparse stacks to per-type counts that wrap the reference's uint8 sums."""
+    from caaa_b200 import synth
+    for rep, max_count in enumerate((1, 3, 12, 60, 255)):
+        bs = synth.battle_states(6000, seed=40 + rep, max_count=max_count)
+        port.set_stream(1, 900 + rep)
+        hostsim.set_stream(1, 900 + rep)
+        for i in range(len(bs)):
+            port.load_state(bs[i], 10**9 + i)
+            hostsim.load_state(bs[i], 10**9 + i)
+            for ph in (9, 11):  # resolve_sea_battles, resolve_land_battles
+                assert port.run_phase(ph) == hostsim.run_phase(ph), (max_count, i, ph)
+            assert np.array_equal(port.get_state(), hostsim.get_state()), (max_count, i)
+            assert port.draws() == hostsim.draws(), (max_count, i)
